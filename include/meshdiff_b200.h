@@ -1,0 +1,97 @@
+/* meshdiff_b200 -- C ABI of the B200-native MeshDiffusion hot path.
+ *
+ * The reference (lzzcd001/MeshDiffusion) has no FFI on this path: its seam is a set of Python callables
+ * (SURVEY.md section 8b). Each entry point below names the reference callable it replaces. All pointers are raw
+ * device pointers unless stated otherwise; `stream` is a cudaStream_t passed as void*. Every function returns 0 on
+ * success and a non-zero code on failure, with a message available from mdb_last_error(). Nothing here
+ * synchronises the stream except where stated, and nothing allocates caller-visible memory.
+ */
+#ifndef MESHDIFF_B200_H
+#define MESHDIFF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* mdb_last_error(void);
+int mdb_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Score network. Replaces DDPMRes64 / DDPMRes128 construction + forward
+ * (lib/diffusion/models/ddpm_res64.py:41-199, ddpm_res128.py:43-215) as created by
+ * mutils.create_model (lib/diffusion/models/utils.py:88-96).
+ */
+typedef struct mdb_unet mdb_unet;
+
+typedef struct mdb_unet_config {
+  int image_size;          /* config.data.image_size */
+  int nf;                  /* config.model.nf */
+  int n_levels;            /* len(config.model.ch_mult) */
+  int ch_mult[8];          /* config.model.ch_mult */
+  int num_res_blocks;      /* config.model.num_res_blocks */
+  int level0_blocks;       /* ddpm_res128.py:98 forces 2 at level 0; -1 = num_res_blocks */
+  int n_attn;
+  int attn_resolutions[4]; /* config.model.attn_resolutions */
+  int num_channels;        /* config.data.num_channels */
+  int stem_ksize;          /* 3 = ddpm_conv3x3 (res64), 5 = ddpm_conv5x5 (res128) */
+  int use_pos_bias;        /* 1: stem adds pos_layer(coords*0) = its bias (ddpm_res64.py:148) */
+  int max_batch;
+  int precision;           /* 0 = bf16 operands, 1 = tf32 operands; fp32 accumulation either way */
+} mdb_unet_config;
+
+int mdb_unet_create(const mdb_unet_config* cfg, mdb_unet** out);
+/* Plan only (parameter table, arena size); no GPU needed. forward()/set_param() must not be called on it. */
+int mdb_unet_create_dry(const mdb_unet_config* cfg, mdb_unet** out);
+void mdb_unet_destroy(mdb_unet* net);
+
+/* Parameter table == the reference state_dict without the DataParallel `module.` prefix
+ * (lib/diffusion/utils.py:23-30). Shapes are the reference's (OIDHW conv weights, [in,out] NIN.W, ...). */
+int mdb_unet_num_params(mdb_unet* net);
+int mdb_unet_param_info(mdb_unet* net, int idx, const char** name, long long* numel, int* ndim, long long* shape8);
+/* load_state_dict: copy one tensor in (src on host if src_is_device == 0). */
+int mdb_unet_set_param(mdb_unet* net, const char* name, const float* src, long long numel, int src_is_device,
+                       void* stream);
+/* state_dict: copy one tensor out; synchronises the stream. */
+int mdb_unet_get_param(mdb_unet* net, const char* name, float* dst, long long numel, int dst_is_device, void* stream);
+/* Re-derive packed weights / constant stem field after parameters changed; synchronises the stream. */
+int mdb_unet_commit(mdb_unet* net, void* stream);
+/* score_model(x, labels): x fp32 NCDHW [B][C][R][R][R], labels fp32 [B], out fp32 NCDHW (ddpm_res64.py:126-199). */
+int mdb_unet_forward(mdb_unet* net, const float* x, const float* labels, float* out, int batch, void* stream);
+int mdb_unet_info(mdb_unet* net, double* flops_per_sample, long long* arena_bytes, int* n_gemm_launches, int* n_steps);
+/* One profiled forward: per-step device milliseconds. names_buf receives '\n'-separated step names. Synchronises. */
+int mdb_unet_profile(mdb_unet* net, const float* x, const float* labels, float* out, int batch, void* stream,
+                     char* names_buf, int names_len, float* ms, int max_steps, int* n_steps);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sampler. Replaces AncestralSamplingPredictor.vpsde_update_fn + get_score_fn + the two grid_mask multiplies of
+ * pc_sampler (lib/diffusion/sampling.py:222-230, 469-478; lib/diffusion/models/utils.py:191-198).
+ * eps = network output, x / x_mean fp32 NCDHW [B][C][V], mask [V]; noise may be NULL (then Philox(seed, offset)).
+ */
+int mdb_sampler_update(const float* eps, float* x, float* x_mean, const float* noise, const float* mask, float beta,
+                       float std, long long voxels, int channels, int batch, unsigned long long seed,
+                       unsigned long long offset, void* stream);
+/* Whole predictor loop of pc_sampler's unconditional branch (sampling.py:469-478) without host round trips:
+ * for i < n_steps: labels[i] -> network -> update. labels/betas/stds are HOST arrays of n_steps floats.
+ * eps_buf: device scratch [B][C][V]; labels_buf: device scratch [B]. Noise is in-kernel Philox. */
+int mdb_sampler_run(mdb_unet* net, float* x, float* x_mean, const float* mask, const float* labels,
+                    const float* betas, const float* stds, int n_steps, int batch, unsigned long long seed,
+                    float* eps_buf, float* labels_buf, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Operator-level entry points (parity tests call these like the reference's renderutils tests call its ops).
+ * Activations are NDHWC in the operand dtype of `precision` (bf16 or fp32).
+ */
+/* nn.Conv3d k in {1,3,5}, stride 1 (padding k/2) or stride 2 (Downsample: pad-high + VALID, layers.py:626-643).
+ * x: [B][Z][Y][X][Cin] (input extents), w: fp32 OIDHW, y: [B][Zo][Yo][Xo][Cout]. Optional: bias [Cout],
+ * rowbias [B][Cout], residual (same layout as y), stats [B][Cout][2] doubles (must be zeroed by the caller). */
+int mdb_conv3d(const void* x, int batch, int cin, int z, int y_, int x_, const float* w, const float* bias, int cout,
+               int ksize, int stride, void* out, const float* rowbias, const void* residual, double* stats,
+               int precision, void* stream);
+/* GroupNorm(32, eps=1e-6) [+ SiLU] from channel statistics: x [B][V][C], stats [B][C][2], y [B][V][C]. */
+int mdb_groupnorm_act(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int batch,
+                      long long voxels, int channels, int silu, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,197 @@
+// extern "C" boundary (include/meshdiff_b200.h). Exceptions never cross it: they become error codes + a message.
+#include "../../include/meshdiff_b200.h"
+#include "unet.h"
+#include <cstring>
+
+using namespace mdb;
+
+static thread_local std::string g_err;
+
+#define MDB_API_BEGIN try {
+#define MDB_API_END                         \
+  }                                         \
+  catch (const std::exception& e) {         \
+    g_err = e.what();                       \
+    return 1;                               \
+  }                                         \
+  catch (...) {                             \
+    g_err = "mdb: unknown error";           \
+    return 2;                               \
+  }                                         \
+  return 0;
+
+struct mdb_unet { UNet* net; };
+
+extern "C" {
+
+const char* mdb_last_error(void) { return g_err.c_str(); }
+int mdb_version(void) { return 100; }
+
+static int create_impl(const mdb_unet_config* c, mdb_unet** out, bool dry) {
+  MDB_API_BEGIN
+  if (!c || !out) throw std::runtime_error("mdb: null argument");
+  UNetConfig u;
+  u.image_size = c->image_size; u.nf = c->nf; u.n_levels = c->n_levels;
+  for (int i = 0; i < 8; ++i) u.ch_mult[i] = c->ch_mult[i];
+  u.num_res_blocks = c->num_res_blocks; u.level0_blocks = c->level0_blocks;
+  u.n_attn = c->n_attn;
+  for (int i = 0; i < 4; ++i) u.attn_resolutions[i] = c->attn_resolutions[i];
+  u.num_channels = c->num_channels; u.stem_ksize = c->stem_ksize; u.use_pos_bias = c->use_pos_bias;
+  u.max_batch = c->max_batch; u.precision = c->precision;
+  auto* h = new mdb_unet;
+  h->net = nullptr;
+  try { h->net = new UNet(u, dry); } catch (...) { delete h; throw; }
+  *out = h;
+  MDB_API_END
+}
+
+int mdb_unet_create(const mdb_unet_config* c, mdb_unet** out) { return create_impl(c, out, false); }
+int mdb_unet_create_dry(const mdb_unet_config* c, mdb_unet** out) { return create_impl(c, out, true); }
+
+void mdb_unet_destroy(mdb_unet* n) {
+  if (!n) return;
+  delete n->net;
+  delete n;
+}
+
+int mdb_unet_num_params(mdb_unet* n) { return n ? (int)n->net->params().size() : -1; }
+
+int mdb_unet_param_info(mdb_unet* n, int idx, const char** name, long long* numel, int* ndim, long long* shape8) {
+  MDB_API_BEGIN
+  const auto& ps = n->net->params();
+  if (idx < 0 || idx >= (int)ps.size()) throw std::runtime_error("mdb: parameter index out of range");
+  if (name) *name = ps[idx].name.c_str();
+  if (numel) *numel = ps[idx].numel;
+  if (ndim) *ndim = (int)ps[idx].shape.size();
+  if (shape8) for (size_t i = 0; i < ps[idx].shape.size() && i < 8; ++i) shape8[i] = ps[idx].shape[i];
+  MDB_API_END
+}
+
+int mdb_unet_set_param(mdb_unet* n, const char* name, const float* src, long long numel, int dev, void* stream) {
+  MDB_API_BEGIN
+  n->net->set_param(name, src, numel, dev != 0, (cudaStream_t)stream);
+  MDB_API_END
+}
+
+int mdb_unet_get_param(mdb_unet* n, const char* name, float* dst, long long numel, int dev, void* stream) {
+  MDB_API_BEGIN
+  n->net->get_param(name, dst, numel, dev != 0, (cudaStream_t)stream);
+  MDB_API_END
+}
+
+int mdb_unet_commit(mdb_unet* n, void* stream) {
+  MDB_API_BEGIN
+  n->net->commit((cudaStream_t)stream);
+  MDB_API_END
+}
+
+int mdb_unet_forward(mdb_unet* n, const float* x, const float* labels, float* out, int B, void* stream) {
+  MDB_API_BEGIN
+  n->net->forward(x, labels, out, B, (cudaStream_t)stream);
+  MDB_API_END
+}
+
+int mdb_unet_info(mdb_unet* n, double* flops, long long* arena, int* ngemm, int* nsteps) {
+  MDB_API_BEGIN
+  if (flops) *flops = n->net->flops_per_sample();
+  if (arena) *arena = (long long)n->net->arena_bytes();
+  if (ngemm) *ngemm = n->net->num_gemm_launches();
+  if (nsteps) *nsteps = n->net->num_steps();
+  MDB_API_END
+}
+
+int mdb_unet_profile(mdb_unet* n, const float* x, const float* labels, float* out, int B, void* stream, char* names,
+                     int names_len, float* ms, int max_steps, int* nsteps) {
+  MDB_API_BEGIN
+  auto r = n->net->profile(x, labels, out, B, (cudaStream_t)stream);
+  std::string all;
+  int k = 0;
+  for (auto& p : r) {
+    if (k >= max_steps) break;
+    all += p.first; all += "\n";
+    ms[k++] = p.second;
+  }
+  if ((int)all.size() + 1 > names_len) throw std::runtime_error("mdb: names buffer too small");
+  std::memcpy(names, all.c_str(), all.size() + 1);
+  if (nsteps) *nsteps = k;
+  MDB_API_END
+}
+
+int mdb_sampler_update(const float* eps, float* x, float* x_mean, const float* noise, const float* mask, float beta,
+                       float stdv, long long V, int C, int B, unsigned long long seed, unsigned long long offset,
+                       void* stream) {
+  MDB_API_BEGIN
+  SamplerUpdateArgs a{};
+  a.eps = eps; a.x = x; a.x_mean = x_mean; a.noise = noise; a.mask = mask; a.beta = beta; a.stdv = stdv;
+  a.V = V; a.C = C; a.seed = seed; a.offset = offset;
+  launch_sampler_update(a, B, (cudaStream_t)stream);
+  MDB_API_END
+}
+
+__global__ void fill_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int mdb_sampler_run(mdb_unet* n, float* x, float* x_mean, const float* mask, const float* labels, const float* betas,
+                    const float* stds, int n_steps, int B, unsigned long long seed, float* eps_buf, float* labels_buf,
+                    void* stream) {
+  MDB_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  const UNetConfig& c = n->net->cfg();
+  const long long V = (long long)c.image_size * c.image_size * c.image_size;
+  for (int i = 0; i < n_steps; ++i) {
+    fill_kernel<<<(B + 127) / 128, 128, 0, s>>>(labels_buf, labels[i], B);
+    n->net->forward(x, labels_buf, eps_buf, B, s);
+    SamplerUpdateArgs a{};
+    a.eps = eps_buf; a.x = x; a.x_mean = x_mean; a.noise = nullptr; a.mask = mask; a.beta = betas[i]; a.stdv = stds[i];
+    a.V = V; a.C = c.num_channels; a.seed = seed; a.offset = (unsigned long long)i;
+    launch_sampler_update(a, B, s);
+  }
+  MDB_API_END
+}
+
+int mdb_conv3d(const void* x, int B, int cin, int z, int y_, int x_, const float* w, const float* bias, int cout,
+               int ksize, int stride, void* out, const float* rowbias, const void* residual, double* stats,
+               int precision, void* stream) {
+  MDB_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  const Precision pr = precision ? kTF32 : kBF16;
+  const int xo = x_ / stride, yo = y_ / stride, zo = z / stride;
+  GemmOp g;
+  g.set_output(pr, xo, yo, zo, B, cout, out, cout, false);
+  Act a; a.ptr = const_cast<void*>(x); a.C = cin; a.X = x_; a.Y = y_; a.Z = z; a.B = B;
+  if (ksize == 1) g.add_pointwise({a}, w, false);
+  else g.add_conv({a}, w, ksize, stride);
+  if (bias) g.set_bias(bias);
+  if (rowbias) g.set_rowbias(rowbias, cout);
+  if (residual) g.set_residual(residual, cout, (long long)xo * yo * zo * cout, false);
+  if (stats) g.set_stats(stats);
+  g.finalize(s, true);
+  g.launch(s);
+  MDB_CUDA_CHECK(cudaStreamSynchronize(s));
+  MDB_API_END
+}
+
+int mdb_groupnorm_act(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int B,
+                      long long V, int C, int silu, int precision, void* stream) {
+  MDB_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  float *scale = nullptr, *shift = nullptr;
+  MDB_CUDA_CHECK(cudaMalloc(&scale, (size_t)B * C * 4));
+  MDB_CUDA_CHECK(cudaMalloc(&shift, (size_t)B * C * 4));
+  GnFinalizeArgs fa{};
+  fa.stats0 = stats; fa.C0 = C; fa.stats1 = nullptr; fa.C1 = 0; fa.gamma = gamma; fa.beta = beta;
+  fa.scale = scale; fa.shift = shift; fa.groups = 32; fa.eps = 1e-6f; fa.count_per_channel = (double)V;
+  launch_gn_finalize(fa, B, s);
+  NormActArgs na{};
+  na.x0 = x; na.C0 = C; na.ld0 = C; na.x1 = nullptr; na.C1 = 0; na.ld1 = 0; na.scale = scale; na.shift = shift;
+  na.y = y; na.voxels = V; na.silu = silu; na.tf32 = precision ? 1 : 0;
+  launch_norm_act(na, B, s);
+  MDB_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(scale);
+  cudaFree(shift);
+  MDB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+#include "elementwise.cuh"
+#include <curand_kernel.h>
+#include <stdexcept>
+#include <string>
+
+namespace mdb {
+
+#define MDB_LAUNCH_CHECK()                                                                              \
+  do {                                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                                \
+    if (_e != cudaSuccess) throw std::runtime_error(std::string("mdb launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int grid_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = 148LL * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__device__ __forceinline__ float round_tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------ GroupNorm finalize
+// nn.GroupNorm(32, C, eps=1e-6) statistics (layers.py:589,652,660; ddpm_res64.py:120): biased variance over
+// (C/32) channels x voxels. Channel sums arrive from the producing GEMM's epilogue in double precision.
+__global__ void gn_finalize_kernel(GnFinalizeArgs a) {
+  const int b = blockIdx.x;
+  const int C = a.C0 + a.C1;
+  const int cpg = C / a.groups;
+  for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+    double s = 0, ss = 0;
+    for (int i = 0; i < cpg; ++i) {
+      const int c = g * cpg + i;
+      const double* p = (c < a.C0) ? a.stats0 + ((long long)b * a.C0 + c) * 2
+                                   : a.stats1 + ((long long)b * a.C1 + (c - a.C0)) * 2;
+      s += p[0]; ss += p[1];
+    }
+    const double n = a.count_per_channel * cpg;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    for (int i = 0; i < cpg; ++i) {
+      const int c = g * cpg + i;
+      const float sc = a.gamma[c] * rstd;
+      a.scale[(long long)b * C + c] = sc;
+      a.shift[(long long)b * C + c] = a.beta[c] - (float)mean * sc;
+    }
+  }
+}
+void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s) {
+  gn_finalize_kernel<<<B, 32, 0, s>>>(a);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ GroupNorm apply (+SiLU), concat-aware
+template <bool TF32>
+__global__ void norm_act_kernel(NormActArgs a, int B) {
+  constexpr int VEC = TF32 ? 4 : 8;  // 16 bytes
+  const int C = a.C0 + a.C1;
+  const int cv = C / VEC;
+  const long long total = (long long)B * a.voxels * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    const long long bv = i / cv;
+    const int b = (int)(bv / a.voxels);
+    const float* sc = a.scale + (long long)b * C + c;
+    const float* sh = a.shift + (long long)b * C + c;
+    float v[VEC];
+    if (TF32) {
+      const float* src = (c < a.C0) ? (const float*)a.x0 + bv * a.ld0 + c : (const float*)a.x1 + bv * a.ld1 + (c - a.C0);
+      float4 t = __ldg((const float4*)src);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      const __nv_bfloat16* src = (c < a.C0) ? (const __nv_bfloat16*)a.x0 + bv * a.ld0 + c
+                                            : (const __nv_bfloat16*)a.x1 + bv * a.ld1 + (c - a.C0);
+      uint4 t = __ldg((const uint4*)src);
+      const __nv_bfloat162* h = (const __nv_bfloat162*)&t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float y = v[j] * __ldg(sc + j) + __ldg(sh + j);
+      if (a.silu) y = silu_f(y);
+      v[j] = y;
+    }
+    if (TF32) {
+      float4 t = make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
+      *((float4*)((float*)a.y + bv * C + c)) = t;
+    } else {
+      uint4 t;
+      __nv_bfloat162* h = (__nv_bfloat162*)&t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *((uint4*)((__nv_bfloat16*)a.y + bv * C + c)) = t;
+    }
+  }
+}
+void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s) {
+  const int vec = a.tf32 ? 4 : 8;
+  const long long total = (long long)B * a.voxels * ((a.C0 + a.C1) / vec);
+  if (a.tf32) norm_act_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(a, B);
+  else norm_act_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(a, B);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample (layers.py:620)
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int Z, int Y, int X, int cv) {
+  const long long total = (long long)B * (2 * Z) * (2 * Y) * (2 * X) * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int c = (int)(r % cv); r /= cv;
+    const int xo = (int)(r % (2 * X)); r /= (2 * X);
+    const int yo = (int)(r % (2 * Y)); r /= (2 * Y);
+    const int zo = (int)(r % (2 * Z)); r /= (2 * Z);
+    const long long src = ((((long long)r * Z + (zo >> 1)) * Y + (yo >> 1)) * X + (xo >> 1)) * cv + c;
+    y[i] = __ldg(x + src);
+  }
+}
+void launch_upsample2x(const void* x, void* y, int B, int Z, int Y, int X, int C, int tf32, cudaStream_t s) {
+  const int cv = C / (tf32 ? 4 : 8);
+  const long long total = (long long)B * 8 * Z * Y * X * cv;
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint4*)x, (uint4*)y, B, Z, Y, X, cv);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ stem im2col
+template <bool TF32>
+__global__ void im2col_kernel(const float* __restrict__ x, void* __restrict__ a, int B, int Cin, int R, int k, int Kpad) {
+  const long long V = (long long)R * R * R;
+  const int T = k * k * k, pad = k / 2;
+  const long long total = (long long)B * V * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % Kpad);
+    long long r = i / Kpad;
+    const int xo = (int)(r % R); r /= R;
+    const int yo = (int)(r % R); r /= R;
+    const int zo = (int)(r % R); r /= R;
+    const int b = (int)r;
+    float v = 0.f;
+    if (col < Cin * T) {
+      const int ci = col / T, tap = col % T;
+      const int kd = tap / (k * k), kh = (tap / k) % k, kw = tap % k;
+      const int zi = zo + kd - pad, yi = yo + kh - pad, xi = xo + kw - pad;
+      if (zi >= 0 && zi < R && yi >= 0 && yi < R && xi >= 0 && xi < R)
+        v = __ldg(x + ((long long)b * Cin + ci) * V + ((long long)zi * R + yi) * R + xi);
+    }
+    if (TF32) ((float*)a)[i] = round_tf32_rna(v);
+    else ((__nv_bfloat16*)a)[i] = __float2bfloat16(v);
+  }
+}
+void launch_im2col(const float* x, void* a, int B, int Cin, int R, int k, int Kpad, int tf32, cudaStream_t s) {
+  const long long total = (long long)B * R * R * R * Kpad;
+  if (tf32) im2col_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(x, a, B, Cin, R, k, Kpad);
+  else im2col_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(x, a, B, Cin, R, k, Kpad);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ row softmax (layers.py:604)
+template <bool TF32>
+__global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L) {
+  __shared__ float red[32];
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    float* p = s + row * L;
+    float vals[16];  // L <= 16 * blockDim.x
+    int n = 0;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) { vals[n] = p[i]; m = fmaxf(m, vals[n]); ++n; }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = 0; j < n; ++j) { vals[j] = __expf(vals[j] - m); sum += vals[j]; }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+    const float inv = 1.f / sum;
+    __syncthreads();  // every thread has consumed its fp32 logits before anyone overwrites the row
+    n = 0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x, ++n) {
+      if (TF32) p[i] = round_tf32_rna(vals[n] * inv);
+      else ((__nv_bfloat16*)p)[i] = __float2bfloat16(vals[n] * inv);
+    }
+  }
+}
+void launch_softmax_rows(float* s, long long rows, int L, int tf32, cudaStream_t st) {
+  if (L > 16 * 256) throw std::runtime_error("mdb: softmax row too long");
+  const int grid = (int)(rows < 148LL * 16 ? rows : 148LL * 16);
+  if (tf32) softmax_rows_kernel<true><<<grid, 256, 0, st>>>(s, rows, L);
+  else softmax_rows_kernel<false><<<grid, 256, 0, st>>>(s, rows, L);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ V transpose: out[b][c][v] = in[b][v][c0+c]
+template <typename T>
+__global__ void transpose_vc_kernel(const T* __restrict__ in, long long ld, int c0, T* __restrict__ out, int V, int C) {
+  __shared__ T tile[32][33];
+  const int b = blockIdx.z;
+  const int v0 = blockIdx.x * 32, cb = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int v = v0 + j, c = cb + threadIdx.x;
+    if (v < V && c < C) tile[j][threadIdx.x] = in[((long long)b * V + v) * ld + c0 + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = cb + j, v = v0 + threadIdx.x;
+    if (v < V && c < C) out[((long long)b * C + c) * V + v] = tile[threadIdx.x][j];
+  }
+}
+void launch_transpose_vc(const void* in, long long ld, int c0, void* out, int B, int V, int C, int tf32, cudaStream_t s) {
+  dim3 grid((V + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (tf32) transpose_vc_kernel<float><<<grid, block, 0, s>>>((const float*)in, ld, c0, (float*)out, V, C);
+  else transpose_vc_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ time embedding MLP
+// get_timestep_embedding (layers.py:542-556): half = nf/2, freq_k = exp(-ln(1e4) * k / (half-1)), [sin, cos];
+// then Linear(nf,4nf) -> SiLU -> Linear(4nf,4nf) (ddpm_res64.py:132-136); ResnetBlockDDPM applies act(temb) before
+// Dense_0 (layers.py:680), so act(temb) is what every consumer needs and is what we store.
+__global__ void temb_kernel(const float* __restrict__ labels, const float* __restrict__ w0, const float* __restrict__ b0,
+                            const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ out, int nf) {
+  extern __shared__ float sm[];
+  float* emb = sm;            // nf
+  float* h1 = sm + nf;        // 4nf
+  const int b = blockIdx.x;
+  const int half = nf / 2;
+  const float t = labels[b];
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+    const int k = i < half ? i : i - half;
+    const float coef = logf(10000.f) / (float)(half - 1);
+    const float f = expf((float)k * -coef);
+    const float arg = t * f;
+    emb[i] = i < half ? sinf(arg) : cosf(arg);
+  }
+  __syncthreads();
+  const int H = 4 * nf;
+  for (int n = threadIdx.x; n < H; n += blockDim.x) {
+    float acc = b0[n];
+    for (int k = 0; k < nf; ++k) acc += w0[(long long)n * nf + k] * emb[k];
+    h1[n] = silu_f(acc);
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < H; n += blockDim.x) {
+    float acc = b1[n];
+    for (int k = 0; k < H; ++k) acc += w1[(long long)n * H + k] * h1[k];
+    out[(long long)b * H + n] = silu_f(acc);
+  }
+}
+void launch_temb(const float* labels, const float* w0, const float* b0, const float* w1, const float* b1, float* out,
+                 int B, int nf, cudaStream_t s) {
+  temb_kernel<<<B, 256, 5 * nf * sizeof(float), s>>>(labels, w0, b0, w1, b1, out, nf);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void dense_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                             float* __restrict__ out, int B, int K, int N) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int o = warp; o < B * N; o += nwarps) {
+    const int b = o / N, n = o % N;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc += w[(long long)n * K + k] * x[(long long)b * K + k];
+    for (int s = 16; s; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) out[(long long)b * N + n] = acc + bias[n];
+  }
+}
+void launch_dense(const float* x, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t s) {
+  dense_kernel<<<grid_for((long long)B * N * 32, 256), 256, 0, s>>>(x, w, bias, out, B, K, N);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+void launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s) {
+  add_vec_kernel<<<grid_for(n, 256), 256, 0, s>>>(a, b, out, n);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ ancestral sampling update
+// Same operation order as the reference's eager fp32 ops (no FMA contraction) so that, given identical eps and
+// noise, x and x_mean are bit-identical: score = -eps/std; x_mean = (x + beta*score)/sqrt(1-beta);
+// x = x_mean + sqrt(beta)*z; both multiplied by grid_mask (sampling.py:222-230, 476-478).
+__global__ void sampler_update_kernel(SamplerUpdateArgs a, int B, float sqrt_1m_beta, float sqrt_beta, float stdv) {
+  const long long per = a.V * a.C;
+  const long long total = per * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % a.V;
+    const float m = __ldg(a.mask + v);
+    const float score = __fdiv_rn(-a.eps[i], stdv);
+    const float xm = __fdiv_rn(__fadd_rn(a.x[i], __fmul_rn(a.beta, score)), sqrt_1m_beta);
+    float z;
+    if (a.noise) {
+      z = a.noise[i];
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(a.seed, (unsigned long long)i, a.offset, &st);
+      z = curand_normal(&st);
+    }
+    const float xn = __fadd_rn(xm, __fmul_rn(sqrt_beta, z));
+    a.x[i] = __fmul_rn(xn, m);
+    a.x_mean[i] = __fmul_rn(xm, m);
+  }
+}
+void launch_sampler_update(const SamplerUpdateArgs& a, int B, cudaStream_t s) {
+  const float one_m = 1.f - a.beta;
+  const float sq1m = sqrtf(one_m), sqb = sqrtf(a.beta);
+  sampler_update_kernel<<<grid_for(a.V * a.C * B, 256), 256, 0, s>>>(a, B, sq1m, sqb, a.stdv);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void mask_mul_kernel(float* x, const float* mask, long long V, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= __ldg(mask + (i % V));
+}
+void launch_mask_mul(float* x, const float* mask, long long V, int C, int B, cudaStream_t s) {
+  const long long total = V * C * B;
+  mask_mul_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, mask, V, total);
+  MDB_LAUNCH_CHECK();
+}
+
+}  // namespace mdb

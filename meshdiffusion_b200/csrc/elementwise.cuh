@@ -1,0 +1,67 @@
+// Bandwidth-bound kernels around the tcgen05 contractions: GroupNorm finalize/apply (+SiLU), nearest 2x upsample,
+// stem im2col, attention softmax / V transpose, time-embedding MLP, ancestral-sampling update.
+// All of these are HBM-roofline kernels: 16-byte vector accesses, grid-stride loops sized to the SM count.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mdb {
+
+struct GnFinalizeArgs {
+  const double* stats0; int C0;   // [B][C0][2]
+  const double* stats1; int C1;   // optional second (concatenated) source
+  const float* gamma; const float* beta;
+  float* scale; float* shift;     // [B][C0+C1]
+  int groups; float eps; double count_per_channel;  // voxels per channel
+};
+void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s);
+
+// y[b][v][c] = act(x[b][v][c] * scale[b][c] + shift[b][c]) over the channel concatenation of up to 2 sources.
+struct NormActArgs {
+  const void* x0; int C0; long long ld0;
+  const void* x1; int C1; long long ld1;
+  const float* scale; const float* shift;  // [B][C0+C1]
+  void* y;                                 // [B][V][C0+C1] dense
+  long long voxels; int silu; int tf32;
+};
+void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s);
+
+void launch_upsample2x(const void* x, void* y, int B, int Z, int Y, int X, int C, int tf32, cudaStream_t s);
+
+// x fp32 NCDHW [B][Cin][R^3] -> A[b][voxel][Kpad], column = cin*k^3 + tap (tap = (kd*k+kh)*k+kw), zero padded.
+void launch_im2col(const float* x, void* a, int B, int Cin, int R, int ksize, int Kpad, int tf32, cudaStream_t s);
+
+// in-place row softmax: rows of L fp32 logits (row stride L floats); writes probabilities in the activation dtype
+// at the start of each row (bf16 rows keep the fp32 row pitch).
+void launch_softmax_rows(float* s, long long rows, int L, int tf32, cudaStream_t st);
+
+// out[b][c][v] = in[b][v][c0 + c]
+void launch_transpose_vc(const void* in, long long ld_in, int c0, void* out, int B, int V, int C, int tf32,
+                         cudaStream_t s);
+
+// temb path (ddpm_res64.py:132-136 + layers.py:542-556,680): act(temb)[B][4nf]
+void launch_temb(const float* labels, const float* w0, const float* b0, const float* w1, const float* b1, float* out,
+                 int B, int nf, cudaStream_t s);
+// out[b][n] = W[n][:] . x[b][:] + bias[n]   (all Dense_0 projections at once)
+void launch_dense(const float* x, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t s);
+
+void launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
+
+// Ancestral-sampling predictor update fused with the score scaling and both mask multiplies
+// (sampling.py:222-230,476-478; models/utils.py:191-198). All fp32, NCDHW [B][4][V]; mask [V].
+struct SamplerUpdateArgs {
+  const float* eps;    // network output
+  float* x;            // in/out state
+  float* x_mean;       // out
+  const float* noise;  // z ~ N(0,1) or null (then Philox below)
+  const float* mask;   // [V]
+  float beta, stdv;    // beta_t, sqrt(1-alpha_bar_t)
+  long long V; int C;
+  unsigned long long seed, offset;  // Philox stream for in-kernel noise
+};
+void launch_sampler_update(const SamplerUpdateArgs& a, int B, cudaStream_t s);
+
+void launch_mask_mul(float* x, const float* mask, long long V, int C, int B, cudaStream_t s);
+
+}  // namespace mdb

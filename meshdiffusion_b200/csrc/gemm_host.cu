@@ -1,0 +1,334 @@
+// Host-side builders for the tcgen05 implicit-GEMM kernel (see gemm_tc.cuh).
+#include "gemm_host.h"
+#include <cstring>
+#include <mutex>
+
+namespace mdb {
+
+// ------------------------------------------------------------------ driver entry point (no libcuda link dependency)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f)
+      throw std::runtime_error("mdb: cuTensorMapEncodeTiled not available (needs an sm_90+ driver)");
+    fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+static void encode_map(CUtensorMap* m, Precision prec, int rank, void* base, const uint64_t* dims,
+                       const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bd[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapDataType dt = prec == kTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = get_encode()(m, dt, rank, base, gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string msg = "mdb: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") rank " +
+                      std::to_string(rank) + " dims";
+    for (int i = 0; i < rank; ++i) msg += " " + std::to_string(dims[i]);
+    msg += " box";
+    for (int i = 0; i < rank; ++i) msg += " " + std::to_string(box[i]);
+    throw std::runtime_error(msg);
+  }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    MDB_CUDA_CHECK(cudaGetDevice(&dev));
+    MDB_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+Geometry pick_geometry(int X, int Y, int Z) {
+  if (Y == 1 && Z == 1) return {128, 1, 1, 1};
+  int bx = X < 8 ? X : 8;
+  int by = 128 / bx;
+  if (by > 16) by = 16;
+  if (by > Y) by = Y;
+  int rem = 128 / (bx * by);
+  int bz = rem < Z ? rem : Z;
+  int bb = rem / bz;
+  return {bx, by, bz, bb};
+}
+
+GemmOp::~GemmOp() {
+  if (d_loads) cudaFree(d_loads);
+  if (d_wpacked && owns_w) cudaFree(d_wpacked);
+}
+
+void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N, void* out, long long osx,
+                                long long osy, long long osz, long long osb, bool out_fp32) {
+  prec = pr;
+  geo = pick_geometry(X, Y, Z);
+  if (geo.bx * geo.by * geo.bz * geo.bb != kBlockM) throw std::runtime_error("mdb: unsupported tile geometry");
+  if (geo.bb > 1 && (geo.bx * geo.by * geo.bz) % 32 != 0)
+    throw std::runtime_error("mdb: multi-sample tiles need a multiple of 32 rows per sample");
+  if (geo.bb > 4) throw std::runtime_error("mdb: at most 4 samples per tile");
+  p.bx = geo.bx; p.by = geo.by; p.bz = geo.bz; p.bb = geo.bb;
+  p.X = X; p.Y = Y; p.Z = Z; p.Bn = B;
+  p.tx = (X + geo.bx - 1) / geo.bx; p.ty = (Y + geo.by - 1) / geo.by;
+  p.tz = (Z + geo.bz - 1) / geo.bz; p.tb = (B + geo.bb - 1) / geo.bb;
+  p.N = N;
+  block_n = N <= 32 ? 32 : 128;
+  p.n_tiles_n = (N + block_n - 1) / block_n;
+  p.out = out;
+  p.osx = osx; p.osy = osy; p.osz = osz; p.osb = osb;
+  p.out_fp32 = out_fp32 ? 1 : 0;
+  p.alpha = 1.f;
+  p.ocs = 1;
+  p.kb_elems = kb_elems(prec);
+}
+
+void GemmOp::set_output(Precision pr, int X, int Y, int Z, int B, int N, void* out, long long ldc, bool out_fp32) {
+  set_output_strided(pr, X, Y, Z, B, N, out, ldc, ldc * X, ldc * X * Y, ldc * X * Y * Z, out_fp32);
+}
+
+int GemmOp::add_amap(const Act& a, int halo, int sub, int px, int py, int pz) {
+  if (n_amaps >= kMaxAMaps) throw std::runtime_error("mdb: too many A tensor maps");
+  if (halo > 0 && (geo.bz != 1 || geo.bb != 1)) throw std::runtime_error("mdb: halo needs a (bx,by,1,1) tile");
+  const long long es = esize(prec);
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  char* base = static_cast<char*>(a.ptr);
+  if (sub == 1) {
+    dims[0] = a.C; dims[1] = a.X; dims[2] = a.Y; dims[3] = a.Z; dims[4] = a.B;
+    strides[0] = a.row() * es; strides[1] = strides[0] * a.X; strides[2] = strides[1] * a.Y; strides[3] = strides[2] * a.Z;
+  } else {
+    dims[0] = a.C; dims[1] = (a.X - px + sub - 1) / sub; dims[2] = (a.Y - py + sub - 1) / sub;
+    dims[3] = (a.Z - pz + sub - 1) / sub; dims[4] = a.B;
+    const long long sx = a.row() * es, sy = sx * a.X, sz = sy * a.Y, sb = sz * a.Z;
+    strides[0] = sx * sub; strides[1] = sy * sub; strides[2] = sz * sub; strides[3] = sb;
+    base += px * sx + py * sy + pz * sz;
+  }
+  box[0] = kb_elems(prec); box[1] = geo.bx; box[2] = geo.by + halo; box[3] = geo.bz; box[4] = geo.bb;
+  encode_map(&p.amap[n_amaps], prec, 5, base, dims, strides, box);
+  return n_amaps++;
+}
+
+void GemmOp::add_load(int tmap, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc, int wc0,
+                      int tap0, int tapj) {
+  if ((int)loads.size() >= kMaxLoads) throw std::runtime_error("mdb: load table overflow");
+  if (rows > kAStageRows) throw std::runtime_error("mdb: A box exceeds the stage size");
+  LoadEntry e{};
+  e.tmap = (uint8_t)tmap; e.nk = (uint8_t)nk; e.rows = (uint8_t)rows; e.jrows = (uint8_t)jrows;
+  e.dx = (int8_t)dx; e.dy = (int8_t)dy; e.dz = (int8_t)dz; e.wsrc = (uint8_t)wsrc;
+  e.c0 = (uint16_t)c0; e.wc0 = (uint16_t)wc0; e.tap0 = (uint8_t)tap0; e.tapj = (uint8_t)tapj;
+  loads.push_back(e);
+  ksteps += nk;
+}
+
+void GemmOp::add_conv(const std::vector<Act>& srcs, const float* w, int k, int stride) {
+  const int KB = kb_elems(prec);
+  int ctot = 0;
+  for (auto& s : srcs) ctot += s.C;
+  const int T = k * k * k;
+  const int ws = add_wsrc({w, 1LL * ctot * T, (long long)T, 1, ctot});
+  const int pad = k / 2;
+  flops += 2.0 * p.X * p.Y * p.Z * p.Bn * (double)p.N * ctot * T;
+  int coff = 0;
+  if (stride == 1) {
+    const bool reuse = geo.bz == 1 && geo.bb == 1 && geo.bx * (geo.by + k - 1) <= kAStageRows && p.Y >= geo.by;
+    for (auto& s : srcs) {
+      const int tm = add_amap(s, reuse ? k - 1 : 0);
+      for (int c0 = 0; c0 < s.C; c0 += KB) {
+        if (reuse) {
+          for (int dz = 0; dz < k; ++dz)
+            for (int dx = 0; dx < k; ++dx)
+              add_load(tm, k, geo.bx * (geo.by + k - 1), geo.bx, dx - pad, -pad, dz - pad, c0, ws, coff + c0,
+                       (dz * k) * k + dx, k);
+        } else {
+          for (int dz = 0; dz < k; ++dz)
+            for (int dy = 0; dy < k; ++dy)
+              for (int dx = 0; dx < k; ++dx)
+                add_load(tm, 1, kBlockM, 0, dx - pad, dy - pad, dz - pad, c0, ws, coff + c0, (dz * k + dy) * k + dx, 0);
+        }
+      }
+      coff += s.C;
+    }
+  } else if (stride == 2) {
+    // layers.py:626-643: pad one voxel on the high side only, then stride-2 VALID conv: in = 2*o + d.
+    // Tap d reads the parity-(d&1) sub-grid at coordinate o + (d>>1); coordinate == sub-grid size -> zero fill = pad.
+    if (k != 3) throw std::runtime_error("mdb: stride-2 conv supports k=3 only");
+    for (auto& s : srcs) {
+      int tm[8];
+      for (int par = 0; par < 8; ++par) tm[par] = add_amap(s, 0, 2, par & 1, (par >> 1) & 1, (par >> 2) & 1);
+      for (int c0 = 0; c0 < s.C; c0 += KB)
+        for (int dz = 0; dz < 3; ++dz)
+          for (int dy = 0; dy < 3; ++dy)
+            for (int dx = 0; dx < 3; ++dx) {
+              const int par = (dx & 1) | ((dy & 1) << 1) | ((dz & 1) << 2);
+              add_load(tm[par], 1, kBlockM, 0, dx >> 1, dy >> 1, dz >> 1, c0, ws, coff + c0, (dz * 3 + dy) * 3 + dx, 0);
+            }
+      coff += s.C;
+    }
+  } else {
+    throw std::runtime_error("mdb: unsupported stride");
+  }
+}
+
+void GemmOp::add_pointwise(const std::vector<Act>& srcs, const float* w, bool w_in_out) {
+  int ctot = 0;
+  for (auto& s : srcs) ctot += s.C;
+  if (!w) { add_pointwise_w(srcs, nullptr); return; }
+  WSrc ws = w_in_out ? WSrc{w, 1, (long long)p.N, 0, ctot} : WSrc{w, (long long)ctot, 1, 0, ctot};
+  add_pointwise_w(srcs, &ws);
+}
+
+void GemmOp::add_pointwise_w(const std::vector<Act>& srcs, const WSrc* w) {
+  const int KB = kb_elems(prec);
+  int ctot = 0;
+  for (auto& s : srcs) ctot += s.C;
+  int ws = 0;
+  if (w) ws = add_wsrc(*w);
+  flops += 2.0 * p.X * p.Y * p.Z * p.Bn * (double)p.N * ctot;
+  int coff = 0;
+  for (auto& s : srcs) {
+    const int tm = add_amap(s, 0);
+    for (int c0 = 0; c0 < s.C; c0 += KB) add_load(tm, 1, kBlockM, 0, 0, 0, 0, c0, ws, coff + c0, 0, 0);
+    coff += s.C;
+  }
+}
+
+void GemmOp::set_residual(const void* res, long long ldr, long long batch_stride, bool fp32) {
+  p.res = res;
+  p.rsx = ldr; p.rsy = ldr * p.X; p.rsz = ldr * p.X * p.Y; p.rsb = batch_stride;
+  p.res_fp32 = fp32 ? 1 : 0;
+}
+
+void GemmOp::encode_bmap(void* ptr, int K, int N, int batch, long long rsb, long long bsb) {
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)batch};
+  uint64_t strides[2] = {(uint64_t)rsb, (uint64_t)bsb};
+  uint32_t box[3] = {(uint32_t)kb_elems(prec), (uint32_t)block_n, 1};
+  encode_map(&p.bmap, prec, 3, ptr, dims, strides, box);
+}
+
+void GemmOp::set_b_activation(void* ptr, int K, int N, int batch, long long rs, long long bs) {
+  b_from_act = true;
+  p.b_batched = 1;
+  const long long es = esize(prec);
+  encode_bmap(ptr, K, N, batch, rs * es, bs * es);
+}
+
+// ------------------------------------------------------------------ weight packing (device gather)
+struct PackWSrc { const float* ptr; long long sn, sc, st; int cvalid; };
+struct PackArgs { PackWSrc w[4]; };
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+template <bool TF32>
+__global__ void pack_weights_kernel(const LoadEntry* __restrict__ loads, const int* __restrict__ ks2load,
+                                    const int* __restrict__ load_ks0, PackArgs args, int N, int ksteps, int KB,
+                                    void* __restrict__ out) {
+  const long long ktot = 1LL * ksteps * KB;
+  const long long total = ktot * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / ktot);
+    const long long k = idx % ktot;
+    const int ks = (int)(k / KB), cc = (int)(k % KB);
+    const int l = ks2load[ks];
+    const LoadEntry e = loads[l];
+    const int j = ks - load_ks0[l];
+    const int tap = e.tap0 + j * e.tapj;
+    const int c = e.wc0 + cc;
+    const PackWSrc w = args.w[e.wsrc];
+    float v = 0.f;
+    if (c < w.cvalid) v = w.ptr[n * w.sn + c * w.sc + tap * w.st];
+    if (TF32) reinterpret_cast<float*>(out)[idx] = round_tf32(v);
+    else reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16(v);
+  }
+}
+
+void GemmOp::repack(cudaStream_t stream) {
+  if (b_from_act) return;
+  std::vector<int> ks2load, ks0;
+  for (size_t l = 0; l < loads.size(); ++l) {
+    ks0.push_back((int)ks2load.size());
+    for (int j = 0; j < loads[l].nk; ++j) ks2load.push_back((int)l);
+  }
+  int *d_a = nullptr, *d_b = nullptr;
+  MDB_CUDA_CHECK(cudaMalloc(&d_a, ks2load.size() * sizeof(int)));
+  MDB_CUDA_CHECK(cudaMalloc(&d_b, ks0.size() * sizeof(int)));
+  MDB_CUDA_CHECK(cudaMemcpyAsync(d_a, ks2load.data(), ks2load.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  MDB_CUDA_CHECK(cudaMemcpyAsync(d_b, ks0.data(), ks0.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  if (wsrcs.size() > 4) throw std::runtime_error("mdb: too many weight sources");
+  PackArgs args{};
+  for (size_t i = 0; i < wsrcs.size(); ++i) args.w[i] = {wsrcs[i].ptr, wsrcs[i].sn, wsrcs[i].sc, wsrcs[i].st, wsrcs[i].cvalid};
+  const long long total = 1LL * ksteps * kb_elems(prec) * p.N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (prec == kTF32)
+    pack_weights_kernel<true><<<blocks, 256, 0, stream>>>(d_loads, d_a, d_b, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+  else
+    pack_weights_kernel<false><<<blocks, 256, 0, stream>>>(d_loads, d_a, d_b, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+  MDB_CUDA_CHECK(cudaGetLastError());
+  MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  cudaFree(d_a);
+  cudaFree(d_b);
+}
+
+void GemmOp::finalize(cudaStream_t stream, bool pack) {
+  if (loads.empty()) throw std::runtime_error("mdb: GemmOp without loads");
+  MDB_CUDA_CHECK(cudaMalloc(&d_loads, loads.size() * sizeof(LoadEntry)));
+  MDB_CUDA_CHECK(cudaMemcpyAsync(d_loads, loads.data(), loads.size() * sizeof(LoadEntry), cudaMemcpyHostToDevice, stream));
+  p.loads = d_loads;
+  p.n_loads = (int)loads.size();
+  if (!b_from_act) {
+    const long long ktot = 1LL * ksteps * kb_elems(prec);
+    const long long bytes = ktot * p.N * esize(prec);
+    MDB_CUDA_CHECK(cudaMalloc(&d_wpacked, bytes));
+    owns_w = true;
+    p.b_batched = 0;
+    encode_bmap(d_wpacked, (int)ktot, p.N, 1, ktot * esize(prec), bytes);
+    if (pack) repack(stream);
+  }
+  MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+template <int BN, bool TF32>
+static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, TF32>;
+  if (!configured) {
+    MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(p);
+  MDB_CUDA_CHECK(cudaGetLastError());
+}
+
+void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
+  GemmParams p = this->p;
+  if (B > 0) {
+    if (B > this->p.Bn) throw std::runtime_error("mdb: batch exceeds the batch the op was built for");
+    p.Bn = B;
+    p.tb = (B + p.bb - 1) / p.bb;
+  }
+  if (out_override) p.out = out_override;
+  const int total = p.tx * p.ty * p.tz * p.tb * p.n_tiles_n;
+  int grid = total < sm_count() ? total : sm_count();
+  const bool tf = prec == kTF32;
+  if (block_n == 32) { if (tf) launch_impl<32, true>(p, grid, stream); else launch_impl<32, false>(p, grid, stream); }
+  else { if (tf) launch_impl<128, true>(p, grid, stream); else launch_impl<128, false>(p, grid, stream); }
+}
+
+}  // namespace mdb

@@ -1,0 +1,109 @@
+// Host-side construction of tcgen05 implicit-GEMM operations: TMA tensor maps, load tables, packed weights.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "gemm_tc.cuh"
+
+namespace mdb {
+
+#define MDB_CUDA_CHECK(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__) + " (" #expr ")");                           \
+  } while (0)
+
+enum Precision { kBF16 = 0, kTF32 = 1 };
+inline int esize(Precision p) { return p == kTF32 ? 4 : 2; }
+inline int kb_elems(Precision p) { return kRowBytes / esize(p); }
+
+// A dense NDHWC activation tensor (channels innermost).
+struct Act {
+  void* ptr = nullptr;
+  int C = 0, X = 0, Y = 0, Z = 0, B = 0;
+  long long ld = 0;  // elements between consecutive voxels (0 = dense, i.e. C)
+  long long row() const { return ld ? ld : C; }
+  long long voxels() const { return 1LL * X * Y * Z; }
+  long long elems() const { return voxels() * B * C; }
+};
+
+// A weight tensor addressed as W[n*sn + c*sc + tap*st]; channels >= cvalid read as zero (K padding).
+struct WSrc {
+  const float* ptr = nullptr;
+  long long sn = 0, sc = 0, st = 0;
+  int cvalid = 0;
+};
+
+struct Geometry { int bx, by, bz, bb; };
+Geometry pick_geometry(int X, int Y, int Z);
+
+class GemmOp {
+ public:
+  GemmParams p{};
+  Precision prec = kBF16;
+  int block_n = 128;
+  std::vector<LoadEntry> loads;
+  std::vector<WSrc> wsrcs;
+  int n_amaps = 0;
+  int ksteps = 0;
+  // device-owned
+  LoadEntry* d_loads = nullptr;
+  void* d_wpacked = nullptr;  // [N][ksteps*KB] in activation dtype
+  bool owns_w = false;
+  double flops = 0;  // algorithmic FLOPs of one launch (2*M*N*K over valid taps, counted densely)
+  std::string name;
+
+  ~GemmOp();
+  GemmOp() = default;
+  GemmOp(const GemmOp&) = delete;
+  GemmOp& operator=(const GemmOp&) = delete;
+
+  // output geometry; must be called first
+  void set_output(Precision prec, int X, int Y, int Z, int B, int N, void* out, long long ldc, bool out_fp32);
+  void set_output_strided(Precision prec, int X, int Y, int Z, int B, int N, void* out, long long osx, long long osy,
+                          long long osz, long long osb, bool out_fp32);
+  // adds a 5-D A tensor map over `a` (optionally a stride-2 parity sub-grid) with a (KB, bx, by+halo, bz, bb) box.
+  int add_amap(const Act& a, int halo_rows_y, int sub_stride = 1, int px = 0, int py = 0, int pz = 0);
+  void add_load(int tmap, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc, int wc0, int tap0,
+                int tapj);
+  int add_wsrc(const WSrc& w) { wsrcs.push_back(w); return (int)wsrcs.size() - 1; }
+
+  // Dense k^3 convolution (cross-correlation, zero padding k/2, stride 1 or 2 [pad-high variant]) over the channel
+  // concatenation of `srcs`; weight OIDHW fp32 [N][sum C][k^3].
+  void add_conv(const std::vector<Act>& srcs, const float* w_oidhw, int ksize, int stride);
+  // 1x1x1 projection of the channel concatenation of `srcs` with W[in][out] (NIN layout) or [out][in] (Linear/conv).
+  void add_pointwise(const std::vector<Act>& srcs, const float* w, bool w_in_out);
+  // same with an explicit weight view (nullptr = no packed weights: B comes from set_b_activation)
+  void add_pointwise_w(const std::vector<Act>& srcs, const WSrc* w);
+
+  // B operand taken from a runtime activation matrix instead of packed weights: Bm[batch][N][K] (K-major).
+  void set_b_activation(void* ptr, int K, int N, int batch, long long row_stride_elems, long long batch_stride_elems);
+
+  void set_bias(const float* bias, bool on_m = false) { p.bias = bias; p.bias_on_m = on_m ? 1 : 0; }
+  void set_rowbias(const float* rb, long long ld) { p.rowbias = rb; p.rowbias_ld = ld; }
+  void set_out_col_stride(long long ocs) { p.ocs = ocs; }
+  void set_residual(const void* res, long long ldr, long long batch_stride, bool fp32);
+  void set_stats(double* stats) { p.stats = stats; }
+  void set_alpha(float a) { p.alpha = a; }
+
+  // Packs weights (device gather kernel), uploads the table, encodes the B map. Call after all add_* calls.
+  void finalize(cudaStream_t stream, bool pack = true);
+  // Re-pack weights only (after a weight reload into the same source buffers).
+  void repack(cudaStream_t stream);
+  // B <= the batch the op was built for; out_override replaces the output pointer (user buffers).
+  void launch(cudaStream_t stream, int B = -1, void* out_override = nullptr) const;
+
+ private:
+  Geometry geo{};
+  bool b_from_act = false;
+  void encode_bmap(void* ptr, int K, int N, int batch, long long row_stride_bytes, long long batch_stride_bytes);
+};
+
+int sm_count();
+
+}  // namespace mdb

@@ -1,0 +1,367 @@
+// Persistent, warp-specialised tcgen05 implicit-GEMM kernel for sm_100a.
+//
+// One kernel serves every dense contraction on the score-network path (reference: nn.Conv3d call sites
+// lib/diffusion/models/layers.py:118-132, NIN layers.py:573-582, attention einsums layers.py:602-606):
+//
+//   D[m, n] = alpha * sum_{k-steps} A_step[m, :] . B[n, kcol(step) : +KB]  (+ bias, + per-sample bias, + residual)
+//
+// * M indexes output voxels. An M-tile is a (bx,by,bz,bb) box of 128 voxels of the NDHWC activation tensor.
+//   A tiles are fetched by TMA straight from the activation tensor as shifted 5-D boxes (zero-filled out of
+//   bounds) -- no im2col buffer exists anywhere.  One A load may carry a halo along the slowest box axis so that
+//   several filter taps (k-steps) reuse the same shared-memory tile through an advanced UMMA descriptor.
+// * B is the packed weight matrix [N][Ktot] (K-major) whose K order is exactly the k-step order of the load
+//   table, fetched by TMA as (KB x BLOCK_N) tiles.
+// * Accumulators live in TMEM (2 stages), read back with tcgen05.ld by 4 epilogue warps which add bias /
+//   time-embedding bias / residual, store NDHWC output and reduce per-(sample, channel) sum and sum-of-squares
+//   for the GroupNorm that follows (warp-shuffle butterfly + shared + one double atomic per channel per tile).
+//
+// Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer, w2 = TMEM allocator, w4..7 = epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace mdb {
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;                       // bytes of K per row per k-step (one 128B swizzle atom)
+constexpr int kAStageRows = 160;                     // 128 + up to 32 halo rows (5-tap reuse)
+constexpr int kAStageBytes = kAStageRows * kRowBytes;  // 20480, multiple of 1024
+constexpr int kMaxLoads = 1024;
+constexpr int kMaxAMaps = 10;
+constexpr int kGemmThreads = 256;
+
+struct __align__(16) LoadEntry {
+  uint8_t tmap;   // index of the A tensor map
+  uint8_t nk;     // k-steps that reuse this A load
+  uint8_t rows;   // rows in the A box (128 or 144)
+  uint8_t jrows;  // smem row advance between consecutive k-steps of this load
+  int8_t dx, dy, dz;  // coordinate offsets added to the tile origin
+  uint8_t wsrc;   // (weight packer) source weight tensor
+  uint16_t c0;    // channel coordinate in the A tensor
+  uint16_t wc0;   // (weight packer) input-channel offset in the weight tensor
+  uint8_t tap0;   // (weight packer) tap index of k-step 0
+  uint8_t tapj;   // (weight packer) tap increment per k-step
+  uint16_t pad;
+};
+static_assert(sizeof(LoadEntry) == 16, "LoadEntry must be 16 bytes");
+
+struct GemmParams {
+  CUtensorMap amap[kMaxAMaps];
+  CUtensorMap bmap;
+  const LoadEntry* loads;
+  int n_loads;
+  int bx, by, bz, bb;  // M-tile box (product 128)
+  int X, Y, Z, Bn;     // output extents
+  int tx, ty, tz, tb;  // tile counts per axis
+  int n_tiles_n;
+  int N;               // valid output columns
+  int b_batched;       // B tensor map has a batch coordinate following the tile's sample
+  int kb_elems;        // K elements per k-step (64 bf16 / 32 tf32)
+  // epilogue
+  void* out;
+  long long osx, osy, osz, osb;  // output element strides per voxel axis
+  long long ocs;                 // output column stride (1 = channels contiguous; else scalar store path)
+  int out_fp32;
+  const float* bias;
+  int bias_on_m;
+  const float* rowbias;  // [Bn][rowbias_ld] per-sample bias (time embedding projection) or null
+  long long rowbias_ld;
+  const void* res;       // residual, same dtype as activations unless res_fp32
+  long long rsx, rsy, rsz, rsb;
+  int res_fp32;
+  float alpha;
+  double* stats;  // [Bn][N][2] (sum, sumsq) or null
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kSA = 3;
+  static constexpr int kSB = (BLOCK_N <= 128) ? 5 : 3;
+  static constexpr int kBStageBytes = BLOCK_N * kRowBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int kStatsFloats = 4 * 2 * BLOCK_N;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kSA * kAStageBytes + kSB * kBStageBytes +
+                                    kMaxLoads * 16 + kStatsFloats * 4 + (2 * kSA + 2 * kSB + 4) * 8 + 16;
+};
+
+template <int BLOCK_N, bool TF32>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + SA * kAStageBytes;
+  LoadEntry* s_loads = reinterpret_cast<LoadEntry*>(smem_b + SB * Cfg::kBStageBytes);
+  float* s_stats = reinterpret_cast<float*>(s_loads + kMaxLoads);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + Cfg::kStatsFloats);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+
+  const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA;
+  const uint32_t b_full = a_empty + 8 * SA, b_empty = b_full + 8 * SB;
+  const uint32_t t_full = b_empty + 8 * SB, t_empty = t_full + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&p.amap[i]);
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(s_tmem));
+  for (int i = threadIdx.x; i < p.n_loads; i += kGemmThreads) s_loads[i] = p.loads[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int tiles_m = p.tx * p.ty * p.tz * p.tb;
+  const int total_tiles = tiles_m * p.n_tiles_n;
+
+  auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0) {
+    int nt = tile % p.n_tiles_n;
+    int mt = tile / p.n_tiles_n;
+    int xt = mt % p.tx; mt /= p.tx;
+    int yt = mt % p.ty; mt /= p.ty;
+    int zt = mt % p.tz; mt /= p.tz;
+    x0 = xt * p.bx; y0 = yt * p.by; z0 = zt * p.bz; b0 = mt * p.bb; n0 = nt * BLOCK_N;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int x0, y0, z0, b0, n0;
+      decode(tile, x0, y0, z0, b0, n0);
+      int kcol = 0;
+      const int bcoord = p.b_batched ? b0 : 0;
+      for (int l = 0; l < p.n_loads; ++l) {
+        const LoadEntry e = s_loads[l];
+        mbar_wait(a_empty + 8 * sa, pa ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(a_full + 8 * sa, static_cast<uint32_t>(e.rows) * kRowBytes);
+          tma_load_5d(&p.amap[e.tmap], a_full + 8 * sa, smem_u32(smem_a + sa * kAStageBytes), e.c0, x0 + e.dx,
+                      y0 + e.dy, z0 + e.dz, b0);
+        }
+        for (int j = 0; j < e.nk; ++j) {
+          mbar_wait(b_empty + 8 * sb, pb ^ 1);
+          if (lane == 0) {
+            mbar_expect_tx(b_full + 8 * sb, Cfg::kBStageBytes);
+            tma_load_3d(&p.bmap, b_full + 8 * sb, smem_u32(smem_b + sb * Cfg::kBStageBytes), kcol, n0, bcoord);
+          }
+          kcol += p.kb_elems;
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc(TF32, kBlockM, BLOCK_N);
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(t_empty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      uint32_t accumulate = 0;
+      for (int l = 0; l < p.n_loads; ++l) {
+        const LoadEntry e = s_loads[l];
+        mbar_wait(a_full + 8 * sa, pa);
+        const uint32_t a_base = smem_u32(smem_a + sa * kAStageBytes);
+        for (int j = 0; j < e.nk; ++j) {
+          mbar_wait(b_full + 8 * sb, pb);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = a_base + j * e.jrows * kRowBytes;
+            const uint32_t b_addr = smem_u32(smem_b + sb * Cfg::kBStageBytes);
+#pragma unroll
+            for (int k = 0; k < kRowBytes / 32; ++k) {
+              umma_ss<TF32>(d_tmem, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32),
+                            idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(b_empty + 8 * sb);
+          }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+        if (lane == 0) umma_commit(a_empty + 8 * sa);
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+      if (lane == 0) umma_commit(t_full + 8 * acc);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;  // 0..127
+    const int rows_per_b = p.bx * p.by * p.bz;
+    const int seg = row / rows_per_b;  // which sample of the tile this row belongs to (warp-uniform by construction)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int x0, y0, z0, b0, n0;
+      decode(tile, x0, y0, z0, b0, n0);
+      int r = row;
+      const int xl = r % p.bx; r /= p.bx;
+      const int yl = r % p.by; r /= p.by;
+      const int zl = r % p.bz; r /= p.bz;
+      const int xg = x0 + xl, yg = y0 + yl, zg = z0 + zl, bg = b0 + r;
+      const bool valid = (xg < p.X) && (yg < p.Y) && (zg < p.Z) && (bg < p.Bn);
+      const long long ooff = xg * p.osx + yg * p.osy + zg * p.osz + bg * p.osb;
+      const long long roff = xg * p.rsx + yg * p.rsy + zg * p.rsz + bg * p.rsb;
+
+      if (p.stats) {
+        for (int i = et; i < Cfg::kStatsFloats; i += 128) s_stats[i] = 0.f;
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(t_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t rr[32];
+        tmem_ld32(t_row + ch * 32, rr);
+        tmem_ld_wait();
+        if (ch == BLOCK_N / 32 - 1) {
+          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+        }
+        const int nb = n0 + ch * 32;
+        if (nb >= p.N) continue;  // warp-uniform
+        const bool full = (nb + 32 <= p.N) && (p.ocs == 1);
+        float v[32];
+        const float mbias = (p.bias && p.bias_on_m && valid) ? __ldg(p.bias + xg) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = __uint_as_float(rr[i]) * p.alpha + mbias;
+          if (full || nb + i < p.N) {
+            if (p.bias && !p.bias_on_m) a += __ldg(p.bias + nb + i);
+            if (p.rowbias && valid) a += __ldg(p.rowbias + static_cast<long long>(bg) * p.rowbias_ld + nb + i);
+          }
+          v[i] = a;
+        }
+        if (p.res && valid) {
+          if (TF32 || p.res_fp32) {
+            const float* rp = reinterpret_cast<const float*>(p.res) + roff + nb;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i) if (nb + i < p.N) v[i] += rp[i];
+            }
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nb;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 f = __bfloat1622float2(h[j]);
+                  v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
+                }
+              }
+            } else {
+              for (int i = 0; i < 32; ++i) if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+            }
+          }
+        }
+        if (valid) {
+          if (TF32 || p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + ooff + nb;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(op)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              for (int i = 0; i < 32; ++i) if (nb + i < p.N) op[i * p.ocs] = v[i];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff + nb;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+                reinterpret_cast<uint4*>(op)[i] = t;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i) if (nb + i < p.N) op[i * p.ocs] = __float2bfloat16(v[i]);
+            }
+          }
+        }
+        if (p.stats) {
+          // Column sums over the warp's 32 rows: butterfly transpose-reduce (31 shuffles per quantity);
+          // afterwards lane i holds the sum of column i.
+          float s[32], ss[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float t = valid ? v[i] : 0.f;
+            s[i] = t; ss[i] = t * t;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_s = hi ? s[i] : s[i + off];
+              const float send_q = hi ? ss[i] : ss[i + off];
+              const float keep_s = hi ? s[i + off] : s[i];
+              const float keep_q = hi ? ss[i + off] : ss[i];
+              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          if (seg < 4) {
+            atomicAdd(&s_stats[(seg * 2 + 0) * BLOCK_N + ch * 32 + lane], s[0]);
+            atomicAdd(&s_stats[(seg * 2 + 1) * BLOCK_N + ch * 32 + lane], ss[0]);
+          }
+        }
+      }
+      if (p.stats) {
+        named_bar_sync(1, 128);
+        for (int i = et; i < p.bb * BLOCK_N; i += 128) {
+          const int sg = i / BLOCK_N, c = i % BLOCK_N;
+          const int bgl = b0 + sg, n = n0 + c;
+          if (bgl < p.Bn && n < p.N) {
+            double* dst = p.stats + (static_cast<long long>(bgl) * p.N + n) * 2;
+            atomicAdd(dst, static_cast<double>(s_stats[(sg * 2 + 0) * BLOCK_N + c]));
+            atomicAdd(dst + 1, static_cast<double>(s_stats[(sg * 2 + 1) * BLOCK_N + c]));
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace mdb

@@ -1,0 +1,69 @@
+"""Operator-level wrappers over the C ABI (used by the parity tests; the engine itself stays inside the library).
+
+Activations are NDHWC torch tensors on the GPU: bfloat16 for precision='bf16', float32 for precision='tf32'.
+"""
+import torch
+
+from . import _native
+
+PRECISIONS = {"bf16": 0, "tf32": 1}
+
+
+def _act_dtype(precision):
+    return torch.bfloat16 if precision == "bf16" else torch.float32
+
+
+def to_ndhwc(x_ncdhw, precision):
+    """[B,C,D,H,W] fp32 -> contiguous [B,D,H,W,C] in the operand dtype."""
+    return x_ncdhw.permute(0, 2, 3, 4, 1).contiguous().to(_act_dtype(precision))
+
+
+def from_ndhwc(y):
+    return y.float().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def conv3d(x, weight, bias=None, stride=1, rowbias=None, residual=None, want_stats=False, precision="bf16"):
+    """nn.Conv3d (k in {1,3,5}; stride 1 'same' or the Downsample stride-2 pad-high variant) on NDHWC input.
+
+    x: [B,Z,Y,X,Cin]; weight: fp32 [Cout,Cin,k,k,k]. Returns y [B,Zo,Yo,Xo,Cout] (and stats [B,Cout,2] float64).
+    """
+    L = _native.lib()
+    assert x.is_cuda and x.is_contiguous() and x.dtype == _act_dtype(precision)
+    B, Z, Y, X, Cin = x.shape
+    Cout, k = weight.shape[0], weight.shape[2]
+    w = weight.detach().float().contiguous()
+    y = torch.empty((B, Z // stride, Y // stride, X // stride, Cout), device=x.device, dtype=x.dtype)
+    stats = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    b = bias.detach().float().contiguous() if bias is not None else None
+    rb = rowbias.detach().float().contiguous() if rowbias is not None else None
+    if residual is not None:
+        assert residual.shape == y.shape and residual.dtype == y.dtype and residual.is_contiguous()
+    _native.check(L.mdb_conv3d(_native.ptr(x), B, Cin, Z, Y, X, _native.ptr(w), _native.ptr(b), Cout, k, stride,
+                               _native.ptr(y), _native.ptr(rb), _native.ptr(residual), _native.ptr(stats),
+                               PRECISIONS[precision], _native.current_stream()))
+    return (y, stats) if want_stats else y
+
+
+def groupnorm_act(x, stats, gamma, beta, silu=True, precision="bf16"):
+    """GroupNorm(32, eps=1e-6) (+SiLU) on NDHWC x using per-channel (sum, sumsq) statistics."""
+    L = _native.lib()
+    B, C = x.shape[0], x.shape[-1]
+    V = x.numel() // (B * C)
+    y = torch.empty_like(x)
+    g = gamma.detach().float().contiguous()
+    bt = beta.detach().float().contiguous()
+    _native.check(L.mdb_groupnorm_act(_native.ptr(x), _native.ptr(stats), _native.ptr(g), _native.ptr(bt), _native.ptr(y),
+                                      B, V, C, 1 if silu else 0, PRECISIONS[precision], _native.current_stream()))
+    return y
+
+
+def sampler_update(eps, x, noise, mask, beta, std, seed=0, offset=0):
+    """In-place ancestral update; returns (x, x_mean). eps/x/noise: fp32 [B,C,R,R,R]; mask fp32 [R,R,R]."""
+    L = _native.lib()
+    B, C = x.shape[0], x.shape[1]
+    V = x[0, 0].numel()
+    x_mean = torch.empty_like(x)
+    _native.check(L.mdb_sampler_update(_native.ptr(eps), _native.ptr(x), _native.ptr(x_mean), _native.ptr(noise),
+                                       _native.ptr(mask), float(beta), float(std), V, C, B, seed, offset,
+                                       _native.current_stream()))
+    return x, x_mean
