@@ -91,6 +91,26 @@ int mdb_conv3d(const void* x, int batch, int cin, int z, int y_, int x_, const f
 int mdb_groupnorm_act(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int batch,
                       long long voxels, int channels, int silu, int precision, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Marching tetrahedra. Replaces DMTet.__call__ (nvdiffrec/lib/geometry/dmtet.py:105-163; tables :34-54, map_uv
+ * :70-99) for a batch of samples over one static tet grid. Integer outputs (faces, uv_idx, face_to_tet,
+ * valid_vert_idx; all int64 like the reference's torch.long) are bit-exact with the reference ordering.
+ */
+/* tets: HOST int32 [F][4] (the npz `indices`); builds the static sorted edge table on the device. */
+int mdb_marching_tets_prepare(const int* tets_host, int n_tets, int n_verts, int max_batch, void** handle);
+void mdb_marching_tets_destroy(void* handle);
+int mdb_marching_tets_info(void* handle, int* n_edges, int* uv_grid_n);
+/* uvs: device fp32 [uv_grid_n^2 * 4][2] */
+int mdb_marching_tets_uvs(void* handle, float* uvs, void* stream);
+/* Phase 1 (synchronises): sdf device fp32 [B][n_verts]; counts_host[b] = {n_verts_out, n_faces, n_valid_verts}. */
+int mdb_marching_tets_count(void* handle, const float* sdf, int batch, int* counts_host, void* stream);
+/* Phase 2: pos device fp32 [B][n_verts][3] (pos_batch_stride in floats; 0 = shared). Outputs packed per sample at
+ * the given element offsets (device int64 [B]). */
+int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batch_stride, const float* sdf, int batch,
+                              float* verts, long long* faces, long long* uv_idx, long long* face_to_tet,
+                              long long* valid_vert_idx, const long long* vert_off, const long long* face_off,
+                              const long long* vv_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

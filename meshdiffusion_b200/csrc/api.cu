@@ -6,6 +6,7 @@
 using namespace mdb;
 
 static thread_local std::string g_err;
+namespace mdb { void set_last_error(const std::string& msg) { g_err = msg; } }
 
 #define MDB_API_BEGIN try {
 #define MDB_API_END                         \
