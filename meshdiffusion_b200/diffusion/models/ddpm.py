@@ -1,0 +1,238 @@
+"""Score networks `ddpm_res64` / `ddpm_res128` backed by the sm_100a engine.
+
+Drop-in for the reference's DDPMRes64 / DDPMRes128 (lib/diffusion/models/ddpm_res64.py:39-199,
+ddpm_res128.py:41-215): same registered names, same `model(x, labels)` call, same parameter names and shapes
+(so reference checkpoints load with `load_state_dict`), same `.mask` / `.coords` / `sigmas` entries. The module
+holds the fp32 master parameters as ordinary torch Parameters; the forward pass runs entirely inside
+libmeshdiff_b200.so (tcgen05 implicit-GEMM convolutions + fused bandwidth kernels). There is no PyTorch or CPU
+fallback: calling the model without the native library and a CUDA device raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import _native
+from . import utils
+
+
+def arch_from_config(config):
+    """Structural hyper-parameters read by the reference constructors (ddpm_res64.py:46-53, ddpm_res128.py:48-55)."""
+    is128 = config.model.name.startswith("ddpm_res128")
+    return dict(
+        image_size=int(config.data.image_size), nf=int(config.model.nf),
+        ch_mult=tuple(int(c) for c in config.model.ch_mult), num_res_blocks=int(config.model.num_res_blocks),
+        attn_resolutions=tuple(int(r) for r in config.model.attn_resolutions),
+        num_channels=int(config.data.num_channels), stem_ksize=5 if is128 else 3, use_pos_bias=not is128,
+        level0_blocks=2 if is128 else int(config.model.num_res_blocks),
+    )
+
+
+def _config_c(arch, max_batch, precision):
+    c = _native.UNetConfigC()
+    c.image_size, c.nf, c.n_levels = arch["image_size"], arch["nf"], len(arch["ch_mult"])
+    for i, v in enumerate(arch["ch_mult"]):
+        c.ch_mult[i] = v
+    c.num_res_blocks, c.level0_blocks = arch["num_res_blocks"], arch["level0_blocks"]
+    c.n_attn = len(arch["attn_resolutions"])
+    for i, v in enumerate(arch["attn_resolutions"]):
+        c.attn_resolutions[i] = v
+    c.num_channels, c.stem_ksize = arch["num_channels"], arch["stem_ksize"]
+    c.use_pos_bias = 1 if arch["use_pos_bias"] else 0
+    c.max_batch, c.precision = max_batch, {"bf16": 0, "tf32": 1}[precision]
+    return c
+
+
+def param_table(arch):
+    """[(name, shape)] in engine order, from a GPU-less dry plan of the native library."""
+    L = _native.lib()
+    h = ctypes.c_void_p()
+    cfg = _config_c(arch, 1, "bf16")
+    _native.check(L.mdb_unet_create_dry(ctypes.byref(cfg), ctypes.byref(h)))
+    try:
+        out = []
+        for i in range(L.mdb_unet_num_params(h)):
+            name, numel, nd = ctypes.c_char_p(), ctypes.c_longlong(), ctypes.c_int()
+            shape = (ctypes.c_longlong * 8)()
+            _native.check(L.mdb_unet_param_info(h, i, ctypes.byref(name), ctypes.byref(numel), ctypes.byref(nd), shape))
+            out.append((name.value.decode(), tuple(int(shape[j]) for j in range(nd.value))))
+        return out
+    finally:
+        L.mdb_unet_destroy(h)
+
+
+def variance_scaling_uniform(shape, scale=1.0, generator=None):
+    """`default_init(scale)` of the reference (layers.py:54-91): fan_avg, uniform, in_axis=1 / out_axis=0."""
+    scale = 1e-10 if scale == 0 else scale
+    receptive = 1
+    for d in shape[2:]:
+        receptive *= d
+    fan_in, fan_out = shape[1] * receptive, shape[0] * receptive
+    bound = math.sqrt(3.0 * scale / ((fan_in + fan_out) / 2.0))
+    return (torch.rand(shape, generator=generator) * 2.0 - 1.0) * bound
+
+
+class _Scope(nn.Module):
+    """Plain container so dotted parameter names become nested state-dict keys."""
+
+
+class ScoreNet(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.arch = arch_from_config(config)
+        self.precision = str(config.model.get("compute_dtype", "tf32")) if hasattr(config.model, "get") else "tf32"
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError("config.model.compute_dtype must be 'bf16' or 'tf32'")
+        self.max_batch = int(config.model.get("engine_max_batch", 0) or 0) if hasattr(config.model, "get") else 0
+        self.scale_by_sigma = bool(config.model.scale_by_sigma)
+        # same buffer as the reference (ddpm_res64.py:44): float64 [num_scales]
+        self.register_buffer("sigmas", torch.tensor(utils.get_sigmas(config)))
+        self._names = []
+        head_idx = None
+        table = param_table(self.arch)
+        for name, _ in table:
+            if name.startswith("all_modules."):
+                head_idx = max(head_idx or 0, int(name.split(".")[1]))
+        # registration order == the reference's parameters() order (own Parameters, pos_layer, mask_layer,
+        # all_modules.*), because the EMA checkpoint stores a positional list (ema.py:91-98)
+        def ref_order(item):
+            n = item[0]
+            if n == "coords": return (0, 0)
+            if n == "mask": return (1, 0)
+            if n.startswith("pos_layer."): return (2, 0)
+            if n.startswith("mask_layer."): return (3, 0)
+            return (4, int(n.split(".")[1]))
+        for name, shape in sorted(table, key=ref_order):
+            self._register(name, self._initial_value(name, shape, head_idx), trainable=name not in ("mask", "coords"))
+        self._handle = None
+        self._engine_batch = 0
+        self._synced = None
+
+    # ---- parameter plumbing -------------------------------------------------------------------------------------
+    def _initial_value(self, name, shape, head_idx):
+        leaf = name.split(".")[-1]
+        if name == "mask" or name == "coords":
+            return torch.zeros(shape)
+        if leaf in ("bias", "b"):
+            return torch.zeros(shape)
+        if "GroupNorm" in name or name == f"all_modules.{head_idx - 1}.weight":
+            return torch.ones(shape)
+        if leaf == "W":  # NIN: init_scale 0.1, except NIN_3 (0.) -- layers.py:574-576,593
+            return variance_scaling_uniform(shape, 0.0 if name.endswith("NIN_3.W") else 0.1)
+        zero_init = name.endswith("Conv_1.weight") or name == f"all_modules.{head_idx}.weight"
+        return variance_scaling_uniform(shape, 0.0 if zero_init else 1.0)
+
+    def _register(self, dotted, value, trainable):
+        parts = dotted.split(".")
+        node = self
+        for p in parts[:-1]:
+            if not hasattr(node, p):
+                node.add_module(p, _Scope())
+            node = getattr(node, p)
+        node.register_parameter(parts[-1], nn.Parameter(value, requires_grad=trainable))
+        self._names.append(dotted)
+
+    def _param(self, dotted):
+        node = self
+        for p in dotted.split("."):
+            node = getattr(node, p)
+        return node
+
+    # ---- engine --------------------------------------------------------------------------------------------------
+    def _ensure_engine(self, batch, device):
+        L = _native.lib()
+        if self._handle is not None and batch <= self._engine_batch:
+            return
+        if device.type != "cuda":
+            raise _native.NativeError("the score network runs only on a CUDA (sm_100a) device; there is no CPU path")
+        self.release_engine()
+        mb = max(batch, self.max_batch)
+        cfg = _config_c(self.arch, mb, self.precision)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _native.check(L.mdb_unet_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._handle, self._engine_batch, self._synced = h, mb, None
+
+    def release_engine(self):
+        if self._handle is not None:
+            _native.lib().mdb_unet_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release_engine()
+        except Exception:
+            pass
+
+    def sync_parameters(self, force=False):
+        """Pushes changed master parameters into the engine and re-derives packed weights / the stem field."""
+        L = _native.lib()
+        versions = [(self._param(n).data_ptr(), self._param(n)._version) for n in self._names]
+        if not force and versions == self._synced:
+            return
+        stream = _native.current_stream()
+        for i, n in enumerate(self._names):
+            if not force and self._synced is not None and versions[i] == self._synced[i]:
+                continue
+            p = self._param(n).detach()
+            src = p.float().contiguous()
+            _native.check(L.mdb_unet_set_param(self._handle, n.encode(), _native.ptr(src), src.numel(),
+                                               1 if src.is_cuda else 0, stream))
+        torch.cuda.current_stream().synchronize()
+        _native.check(L.mdb_unet_commit(self._handle, stream))
+        self._synced = versions
+
+    def forward(self, x, labels):
+        if not x.is_cuda:
+            raise _native.NativeError("the score network runs only on a CUDA (sm_100a) device; there is no CPU path")
+        L = _native.lib()
+        x = x.float().contiguous()
+        labels = labels.to(device=x.device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        with torch.cuda.device(x.device):
+            self._ensure_engine(B, x.device)
+            self.sync_parameters()
+            out = torch.empty_like(x)
+            _native.check(L.mdb_unet_forward(self._handle, _native.ptr(x), _native.ptr(labels), _native.ptr(out), B,
+                                             _native.current_stream()))
+        if self.scale_by_sigma:
+            out = out / self.sigmas.to(out.device)[labels.long(), None, None, None, None].float()
+        return out
+
+    def engine_info(self):
+        L = _native.lib()
+        fl, ar, ng, ns = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+        _native.check(L.mdb_unet_info(self._handle, ctypes.byref(fl), ctypes.byref(ar), ctypes.byref(ng), ctypes.byref(ns)))
+        return dict(flops_per_sample=fl.value, arena_bytes=ar.value, gemm_launches=ng.value, steps=ns.value,
+                    max_batch=self._engine_batch, precision=self.precision)
+
+    def profile(self, x, labels):
+        """One profiled forward: [(step name, device ms)]."""
+        L = _native.lib()
+        B = x.shape[0]
+        self._ensure_engine(B, x.device)
+        self.sync_parameters()
+        out = torch.empty_like(x)
+        names = ctypes.create_string_buffer(1 << 16)
+        ms = (ctypes.c_float * 1024)()
+        n = ctypes.c_int()
+        _native.check(L.mdb_unet_profile(self._handle, _native.ptr(x), _native.ptr(labels), _native.ptr(out), B,
+                                         _native.current_stream(), names, len(names), ms, 1024, ctypes.byref(n)))
+        return list(zip(names.value.decode().strip().split("\n"), [ms[i] for i in range(n.value)]))
+
+
+@utils.register_model(name="ddpm_res64")
+class DDPMRes64(ScoreNet):
+    pass
+
+
+@utils.register_model(name="ddpm_res128")
+class DDPMRes128(ScoreNet):
+    pass
+
+
+# configs/res128.py:40 names 'ddpm_res128_v2' although the reference registers only 'ddpm_res128'
+# (ddpm_res128.py:41); register both so the stock config works.
+utils.register_model(DDPMRes128, name="ddpm_res128_v2")

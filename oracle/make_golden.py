@@ -1,0 +1,202 @@
+"""Pins the oracle against the UNMODIFIED reference and writes the golden vectors under tests/golden/.
+
+Run in the authoring container only (needs /root/reference; the GPU box never sees it):
+
+    python oracle/make_golden.py
+
+What it does, per piece of the hot path:
+  1. imports the reference's own modules from /root/reference (with an `ml_collections` stand-in and
+     `Tensor.cuda` neutralised -- sde_lib.py:189,192 hard-code .cuda()),
+  2. runs reference and oracle on the same seeded inputs on CPU fp32 and ASSERTS they agree,
+  3. stores inputs (or the seeds that generate them) + reference outputs as small fixtures.
+The reference ships no tests / golden vectors for this path, so these files are the pin.
+"""
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from meshdiffusion_b200.compat.install import ensure_ml_collections  # noqa: E402
+
+ensure_ml_collections()
+from oracle import unet_oracle, sampler_oracle, mt_oracle, synth  # noqa: E402
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self  # reference hard-codes .cuda() in table construction
+    from lib.diffusion.models import ddpm_res64, ddpm_res128, utils as rutils  # noqa: F401
+    from lib.diffusion import sde_lib as rsde, sampling as rsampling
+    from configs import res64 as rcfg64, res128 as rcfg128
+    return dict(ddpm_res64=ddpm_res64, ddpm_res128=ddpm_res128, rutils=rutils, rsde=rsde, rsampling=rsampling,
+                rcfg64=rcfg64, rcfg128=rcfg128)
+
+
+def ref_config(ref, name, tiny):
+    cfg = (ref["rcfg128"] if name == "res128" else ref["rcfg64"]).get_config()
+    if name == "res128":
+        cfg.model.name = "ddpm_res128"  # the stock config names an unregistered model
+    if tiny:
+        synth.apply_tiny(cfg, name)
+    cfg.device = torch.device("cpu")
+    return cfg
+
+
+def build_ref_model(ref, cfg):
+    cls = ref["rutils"].get_model(cfg.model.name)
+    torch.manual_seed(0)
+    return cls(cfg).eval()
+
+
+def golden_param_tables(ref):
+    out = {}
+    for name in ("res64", "res128"):
+        cfg = ref_config(ref, name, tiny=False)
+        model = torch.nn.DataParallel(build_ref_model(ref, cfg))
+        sd = model.state_dict()
+        out[name] = dict(
+            state_dict=[(k, list(v.shape), str(v.dtype)) for k, v in sd.items()],
+            trainable=[n for n, p in model.named_parameters() if p.requires_grad],
+        )
+        print(name, len(sd), "state-dict entries;", sum(p.numel() for p in model.parameters() if p.requires_grad), "trainable")
+        del model
+    with open(os.path.join(GOLD, "param_tables.json"), "w") as f:
+        json.dump(out, f)
+
+
+def golden_unet_forward(ref):
+    for name in ("res64", "res128"):
+        cfg = ref_config(ref, name, tiny=True)
+        model = build_ref_model(ref, cfg)
+        sd = synth.synthetic_state_dict(model.state_dict(), seed=11)
+        model.load_state_dict(sd)
+        x, labels = synth.synthetic_inputs(cfg.data.image_size, batch=2, seed=12, mask=sd["mask"])
+        with torch.no_grad():
+            y_ref = model(x, labels)
+            y_orc = unet_oracle.unet_forward(sd, unet_oracle.arch_from_config(cfg), x, labels)
+        err = (y_ref - y_orc).abs().max().item()
+        print(f"unet {name} tiny: |ref| max {y_ref.abs().max():.4f}, oracle-vs-reference max abs diff {err:.3e}")
+        assert err <= 2e-5 * max(1.0, y_ref.abs().max().item()), "oracle U-Net disagrees with the reference"
+        np.savez_compressed(os.path.join(GOLD, f"unet_tiny_{name}.npz"), out=y_ref.numpy(),
+                            checksum=synth.state_checksum(sd), state_seed=11, input_seed=12)
+
+
+def golden_sampler(ref):
+    import tqdm
+    cfg = ref_config(ref, "res64", tiny=True)
+    model = build_ref_model(ref, cfg)
+    sd = synth.synthetic_state_dict(model.state_dict(), seed=21)
+    model.load_state_dict(sd)
+    R, B, n_it = cfg.data.image_size, 2, 4
+    rsde, rsamp = ref["rsde"], ref["rsampling"]
+    sde = rsde.VPSDE(beta_min=cfg.model.beta_min, beta_max=cfg.model.beta_max, N=cfg.model.num_scales)
+    osde = sampler_oracle.VPSDETables(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales)
+    for a, b in ((sde.discrete_betas, osde.discrete_betas), (sde.sqrt_1m_alphas_cumprod, osde.sqrt_1m_alphas_cumprod)):
+        assert torch.equal(a, b), "VP-SDE tables differ"
+    grid_mask = sd["mask"].view(1, R, R, R)
+    real_trange = tqdm.trange
+    rsamp.tqdm.trange = lambda n: range(min(n, n_it))  # first iterations of the N=1000 schedule
+    try:
+        sampler = rsamp.get_pc_sampler(sde, (B, 4, R, R, R), rsamp.get_predictor("ancestral_sampling"),
+                                       rsamp.get_corrector("none"), lambda x: x, snr=cfg.sampling.snr, n_steps=1,
+                                       probability_flow=False, continuous=False, denoise=True, eps=1e-3, device="cpu",
+                                       grid_mask=grid_mask)
+        torch.manual_seed(31)
+        s_ref, _ = sampler(model)
+        torch.manual_seed(31)
+        fn = lambda x, t: unet_oracle.unet_forward(sd, unet_oracle.arch_from_config(cfg), x, t)
+        s_orc = sampler_oracle.pc_sample_uncond(osde, fn, torch.randn(B, 4, R, R, R), grid_mask, torch.randn_like, n_iters=n_it)
+        err = (s_ref - s_orc).abs().max().item()
+        print(f"sampler uncond ({n_it} iters): oracle-vs-reference max abs diff {err:.3e}")
+        assert err <= 1e-4
+        # partial (conditional) branch
+        g = torch.Generator().manual_seed(41)
+        partial = torch.sign(torch.randn(B, 4, R, R, R, generator=g))
+        pmask4 = (torch.rand(1, 1, R, R, R, generator=g) < 0.5).float().expand(B, 4, R, R, R).contiguous()
+        gm5 = sd["mask"].view(1, 1, R, R, R)
+        sampler5 = rsamp.get_pc_sampler(sde, (B, 4, R, R, R), rsamp.get_predictor("ancestral_sampling"),
+                                        rsamp.get_corrector("none"), lambda x: x, snr=cfg.sampling.snr, n_steps=1,
+                                        probability_flow=False, continuous=False, denoise=True, eps=1e-3, device="cpu",
+                                        grid_mask=gm5)
+        torch.manual_seed(32)
+        c_ref, _ = sampler5(model, partial=partial, partial_mask=pmask4, freeze_iters=3)
+        torch.manual_seed(32)
+        c_orc = sampler_oracle.pc_sample_partial(osde, fn, torch.randn(B, 4, R, R, R), gm5, partial, pmask4,
+                                                 torch.randn_like, freeze_iters=3, n_iters=n_it)
+        cerr = (c_ref - c_orc).abs().max().item()
+        print(f"sampler partial ({n_it} iters): oracle-vs-reference max abs diff {cerr:.3e}")
+        assert cerr <= 1e-4
+    finally:
+        rsamp.tqdm.trange = real_trange
+    np.savez_compressed(os.path.join(GOLD, "sampler_tiny.npz"), uncond=s_ref.numpy(), partial=c_ref.numpy(),
+                        checksum=synth.state_checksum(sd), state_seed=21, n_iters=n_it,
+                        betas=sde.discrete_betas.numpy(), sqrt_1m_ac=sde.sqrt_1m_alphas_cumprod.numpy())
+
+
+def load_reference_dmtet():
+    """The DMTet class body (dmtet.py:32-163) depends only on torch/numpy; its module imports kaolin etc., so the
+    class source is exec'd on its own with 'cuda' -> 'cpu'. Nothing from it is written into this repository."""
+    src = open(os.path.join(REF, "nvdiffrec/lib/geometry/dmtet.py")).read().split("\n")
+    start = next(i for i, l in enumerate(src) if l.startswith("class DMTet:"))
+    end = next(i for i, l in enumerate(src) if l.startswith("def compute_sdf") or (i > start and l.startswith("class ")) or l.startswith("# Regularizer") or l.startswith("def ") and i > start)
+    body = "\n".join(src[start:end]).replace("'cuda'", "'cpu'").replace('"cuda"', '"cpu"')
+    ns = {"torch": torch, "np": np}
+    exec(compile(body, "reference_dmtet", "exec"), ns)
+    return ns["DMTet"]
+
+
+def golden_marching_tets():
+    DMTet = load_reference_dmtet()
+    mt = DMTet()
+    tets = np.load(os.path.join(REF, "nvdiffrec/data/tets/64_tets_cropped.npz"))
+    verts, idx = tets["vertices"], tets["indices"]
+    cases = {}
+    for case, seed in (("sphere", 0), ("noisy", 1)):
+        sdf, pos = synth.synthetic_dmtet(verts, seed=seed, noisy=(case == "noisy"))
+        with torch.no_grad():
+            r = mt(torch.tensor(pos), torch.tensor(sdf), torch.tensor(idx).long())
+        r = [t.numpy() for t in r]
+        o = mt_oracle.marching_tets(pos, sdf, idx)
+        names = ["verts", "faces", "uvs", "uv_idx", "face_to_valid_tet", "valid_vert_idx"]
+        for n, a, b in zip(names, r, o):
+            assert a.shape == b.shape, (case, n, a.shape, b.shape)
+            if a.dtype.kind in "iu":
+                assert np.array_equal(a, b), f"marching tets {case}: integer output {n} differs"
+            else:
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-7), f"marching tets {case}: {n} differs"
+        print(f"marching tets {case}: {r[0].shape[0]} verts, {r[1].shape[0]} faces -- oracle == reference")
+        cases[case + "_verts"] = r[0]
+        cases[case + "_faces"] = r[1].astype(np.int32)
+        cases[case + "_uv_idx"] = r[3].astype(np.int32)
+        cases[case + "_face_to_valid_tet"] = r[4].astype(np.int32)
+        cases[case + "_valid_vert_idx"] = r[5].astype(np.int32)
+        cases[case + "_uvs_shape"] = np.array(r[2].shape)
+        cases[case + "_uvs_head"] = r[2][:64]
+        cases[case + "_uvs_tail"] = r[2][-64:]
+        cases[case + "_uvs_sum"] = np.array([r[2].astype(np.float64).sum()])
+    np.savez_compressed(os.path.join(GOLD, "marching_tets_64.npz"), **cases)
+    # grid mask derivable from the tet grid (data/get_tet_mask.py): check against the shipped mask
+    coords = mt_oracle.grid_coords_of_tet_vertices(verts)
+    mask = np.zeros((64, 64, 64), np.float32)
+    mask[coords[:, 0], coords[:, 1], coords[:, 2]] = 1
+    ref_mask = torch.load(os.path.join(REF, "data/grid_mask_64.pt"), map_location="cpu").numpy()
+    assert np.array_equal(mask, ref_mask), "grid mask derived from the tet grid differs from data/grid_mask_64.pt"
+    print("grid_mask_64 == scatter of tet vertices:", int(mask.sum()), "voxels")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    ref = import_reference()
+    golden_marching_tets()
+    golden_unet_forward(ref)
+    golden_sampler(ref)
+    golden_param_tables(ref)
+    print("golden vectors written to", GOLD)
