@@ -1,0 +1,140 @@
+"""CPU: host-side logic -- parameter table vs the reference's state_dict, checkpoint layout, config surface, CLI,
+registries, EMA arithmetic, and a world_size-2 gloo run of the batch-sharded sampler plumbing."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD, ROOT, full_config, tiny_config
+
+
+@pytest.mark.parametrize("name", ["res64", "res128"])
+def test_state_dict_matches_reference_layout(name):
+    """Keys (with the DataParallel 'module.' prefix), order, shapes and dtypes of the reference's state_dict, and the
+    order of trainable parameters that the positional EMA list depends on (golden from the reference constructor)."""
+    from meshdiffusion_b200.diffusion.models import utils as mutils
+    gold = json.load(open(os.path.join(GOLD, "param_tables.json")))[name]
+    cfg = full_config(name)
+    cfg.device = torch.device("cpu")
+    with torch.device("meta"):
+        pass
+    model = mutils.create_model(cfg)
+    sd = model.state_dict()
+    ours = {k: (list(v.shape), str(v.dtype)) for k, v in sd.items()}
+    ref = {k: (shape, dt) for k, shape, dt in gold["state_dict"]}
+    assert set(ours) == set(ref), (sorted(set(ref) - set(ours))[:5], sorted(set(ours) - set(ref))[:5])
+    for k in ref:
+        assert ours[k] == ref[k], (k, ours[k], ref[k])
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert trainable == gold["trainable"]
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from meshdiffusion_b200.diffusion import losses
+    from meshdiffusion_b200.diffusion.models import utils as mutils
+    from meshdiffusion_b200.diffusion.models.ema import ExponentialMovingAverage
+    from meshdiffusion_b200.diffusion.utils import restore_checkpoint, save_checkpoint
+    cfg = tiny_config()
+    cfg.device = torch.device("cpu")
+    model = mutils.create_model(cfg)
+    opt = losses.get_optimizer(cfg, model.parameters())
+    ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    ema.update(model.parameters())
+    state = dict(optimizer=opt, model=model, ema=ema, step=7)
+    path = os.path.join(tmp_path, "checkpoints-meta", "checkpoint.pth")
+    save_checkpoint(path, state)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(raw) == {"optimizer", "model", "ema", "step"} and raw["step"] == 7
+    assert all(k.startswith("module.") for k in raw["model"])
+    assert set(raw["ema"]) == {"decay", "num_updates", "shadow_params"} and raw["ema"]["num_updates"] == 1
+    model2 = mutils.create_model(cfg)
+    state2 = dict(optimizer=losses.get_optimizer(cfg, model2.parameters()), model=model2,
+                  ema=ExponentialMovingAverage(model2.parameters(), decay=0.5), step=0)
+    state2 = restore_checkpoint(path, state2, device="cpu")
+    assert state2["step"] == 7 and state2["ema"].decay == cfg.model.ema_rate
+    for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # missing file: warning + unchanged state (lib/diffusion/utils.py:7-13)
+    assert restore_checkpoint(os.path.join(tmp_path, "nope", "x.pth"), state2, "cpu")["step"] == 7
+
+
+def test_ema_arithmetic():
+    from meshdiffusion_b200.diffusion.models.ema import ExponentialMovingAverage
+    p = [torch.nn.Parameter(torch.ones(4)), torch.nn.Parameter(torch.zeros(3), requires_grad=False)]
+    ema = ExponentialMovingAverage(p, decay=0.9999)
+    assert len(ema.shadow_params) == 1
+    p[0].data.fill_(3.0)
+    ema.update(p)  # decay_t = min(0.9999, 2/11)
+    d = 2.0 / 11.0
+    assert torch.allclose(ema.shadow_params[0], torch.full((4,), 1.0 - (1 - d) * (1.0 - 3.0)))
+
+
+def test_config_surface_and_cli_overrides():
+    import main_diffusion
+    path, mode, ov = main_diffusion.parse_args(["--config=configs/res64.py", "--mode=uncond_gen", "--config.eval.batch_size=7",
+                                                "--config.eval.eval_dir=/tmp/x", "--config.new.key=(1,2)"])
+    assert mode == "uncond_gen" and ("eval.batch_size", 7) in ov and ("new.key", (1, 2)) in ov
+    cfg = main_diffusion.load_config_file(os.path.join(ROOT, path))
+    for k, v in ov:
+        cfg.set_by_path(k, v)
+    assert cfg.eval.batch_size == 7 and cfg.new.key == (1, 2) and cfg.eval.eval_dir == "/tmp/x"
+    assert cfg.model.ch_mult == (1, 1, 2, 4, 4) and cfg.sampling.predictor == "ancestral_sampling" and cfg.optim.lr == 2e-5
+    with pytest.raises(SystemExit):
+        main_diffusion.parse_args(["--config=c.py", "--mode=bogus"])
+
+
+def test_registries():
+    from meshdiffusion_b200.diffusion import sampling
+    from meshdiffusion_b200.diffusion.models import ddpm, utils as mutils
+    assert mutils.get_model("ddpm_res64") is ddpm.DDPMRes64
+    assert mutils.get_model("ddpm_res128_v2") is mutils.get_model("ddpm_res128")
+    for n in ("euler_maruyama", "reverse_diffusion", "ancestral_sampling", "none"):
+        assert sampling.get_predictor(n)
+    for n in ("langevin", "ald", "none"):
+        assert sampling.get_corrector(n)
+    with pytest.raises(ValueError):
+        mutils.register_model(ddpm.DDPMRes64, name="ddpm_res64")
+
+
+def test_score_net_refuses_cpu():
+    from meshdiffusion_b200 import _native
+    from meshdiffusion_b200.diffusion.models import utils as mutils
+    cfg = tiny_config()
+    cfg.device = torch.device("cpu")
+    model = mutils.create_model(cfg)
+    with pytest.raises(_native.NativeError):
+        model(torch.zeros(1, 4, 16, 16, 16), torch.zeros(1))
+
+
+GLOO_CHILD = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# the sampler shards the batch with no data-path collective: only timing / bookkeeping crosses ranks
+from meshdiffusion_b200.diffusion import sde_lib
+sde = sde_lib.VPSDE(device="cpu")
+torch.manual_seed(42 + rank)
+x = torch.randn(2, 4, 8, 8, 8)
+t = torch.tensor([float(rank + 1)])
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+gathered = [torch.zeros(2, 4, 8, 8, 8) for _ in range(world)]
+dist.all_gather(gathered, x)
+assert t.item() == world and not torch.equal(gathered[0], gathered[1])
+print("RANK_OK", rank, float(sde.discrete_betas[0]))
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_world_size_2_gloo_plumbing(tmp_path):
+    script = os.path.join(tmp_path, "child.py")
+    open(script, "w").write(GLOO_CHILD)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("RANK_OK") == 2

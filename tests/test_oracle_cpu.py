@@ -1,0 +1,69 @@
+"""CPU: the oracle reproduces the golden vectors that oracle/make_golden.py produced from the REFERENCE modules."""
+import numpy as np
+import torch
+
+from helpers import load_golden, tiny_config
+from oracle import mt_oracle, sampler_oracle, synth, unet_oracle
+
+
+def _tiny_sd(name, seed):
+    from meshdiffusion_b200.diffusion.models import utils as mutils
+    cfg = tiny_config(name)
+    cfg.device = torch.device("cpu")
+    net = mutils.create_model(cfg, use_parallel=False)
+    sd = synth.synthetic_state_dict({k: v.detach() for k, v in net.state_dict().items()}, seed=seed)
+    return cfg, sd
+
+
+def test_unet_oracle_matches_reference_golden():
+    for name in ("res64", "res128"):
+        gold = load_golden(f"unet_tiny_{name}.npz")
+        cfg, sd = _tiny_sd(name, int(gold["state_seed"]))
+        assert np.abs(synth.state_checksum(sd) - gold["checksum"]).max() < 1e-6
+        x, labels = synth.synthetic_inputs(cfg.data.image_size, 2, int(gold["input_seed"]), sd["mask"])
+        with torch.no_grad():
+            out = unet_oracle.unet_forward(sd, unet_oracle.arch_from_config(cfg), x, labels)
+        assert np.abs(out.numpy() - gold["out"]).max() < 5e-5
+
+
+def test_sampler_oracle_matches_reference_golden():
+    gold = load_golden("sampler_tiny.npz")
+    cfg, sd = _tiny_sd("res64", int(gold["state_seed"]))
+    R, B, n_it = 16, 2, int(gold["n_iters"])
+    sde = sampler_oracle.VPSDETables(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales)
+    assert np.array_equal(sde.discrete_betas.numpy(), gold["betas"])
+    assert np.array_equal(sde.sqrt_1m_alphas_cumprod.numpy(), gold["sqrt_1m_ac"])
+    fn = lambda x, t: unet_oracle.unet_forward(sd, unet_oracle.arch_from_config(cfg), x, t)
+    with torch.no_grad():
+        torch.manual_seed(31)
+        out = sampler_oracle.pc_sample_uncond(sde, fn, torch.randn(B, 4, R, R, R), sd["mask"].view(1, R, R, R), torch.randn_like, n_iters=n_it)
+        assert np.abs(out.numpy() - gold["uncond"]).max() < 1e-4
+        g = torch.Generator().manual_seed(41)
+        partial = torch.sign(torch.randn(B, 4, R, R, R, generator=g))
+        pmask = (torch.rand(1, 1, R, R, R, generator=g) < 0.5).float().expand(B, 4, R, R, R).contiguous()
+        torch.manual_seed(32)
+        out = sampler_oracle.pc_sample_partial(sde, fn, torch.randn(B, 4, R, R, R), sd["mask"].view(1, 1, R, R, R), partial, pmask,
+                                               torch.randn_like, freeze_iters=3, n_iters=n_it)
+        assert np.abs(out.numpy() - gold["partial"]).max() < 1e-4
+
+
+def test_marching_tets_oracle_matches_reference_golden():
+    from meshdiffusion_b200.geometry import dmtet
+    gold = load_golden("marching_tets_64.npz")
+    verts, idx = dmtet.load_tet_grid(64)
+    for case, seed, noisy in (("sphere", 0, False), ("noisy", 1, True)):
+        sdf, pos = synth.synthetic_dmtet(verts, seed=seed, noisy=noisy)
+        v, f, uvs, uvi, f2t, vvi = mt_oracle.marching_tets(pos, sdf, idx)
+        assert np.array_equal(f, gold[case + "_faces"])
+        assert np.array_equal(uvi, gold[case + "_uv_idx"])
+        assert np.array_equal(f2t, gold[case + "_face_to_valid_tet"])
+        assert np.array_equal(vvi, gold[case + "_valid_vert_idx"])
+        assert np.allclose(v, gold[case + "_verts"], rtol=1e-6, atol=1e-7)
+        assert tuple(uvs.shape) == tuple(gold[case + "_uvs_shape"])
+
+
+def test_grid_mask_from_tets_has_reference_population():
+    from meshdiffusion_b200.geometry import dmtet
+    m = dmtet.grid_mask_from_tets(64)
+    assert int(m.sum()) == 30512 and m.shape == (64, 64, 64)  # 30 512 of 262 144 voxels
+    assert int(dmtet.grid_mask_from_tets(128).sum()) == 253024
