@@ -182,6 +182,9 @@ def run_ours(args):
     if rank == 0:
         labels = vec * labels_all[W]
         prof = net.profile(x, labels)
+        if args.dump_profile:
+            with open(args.dump_profile, "w") as f:
+                json.dump(prof, f)
         launches_per_forward = len(prof) + 2  # + stats memset, + second kernel of the temb step
         conv_ms = sum(t for n, t in prof if _is_conv_gemm(n))
         all_gemm_ms = sum(t for n, t in prof if _is_gemm(n))
@@ -313,6 +316,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event times of one forward as JSON")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

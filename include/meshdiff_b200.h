@@ -83,12 +83,14 @@ int mdb_sampler_run(mdb_unet* net, float* x, float* x_mean, const float* mask, c
  */
 /* nn.Conv3d k in {1,3,5}, stride 1 (padding k/2) or stride 2 (Downsample: pad-high + VALID, layers.py:626-643).
  * x: [B][Z][Y][X][Cin] (input extents), w: fp32 OIDHW, y: [B][Zo][Yo][Xo][Cout]. Optional: bias [Cout],
- * rowbias [B][Cout], residual (same layout as y), stats [B][Cout][2] doubles (must be zeroed by the caller). */
+ * rowbias [B][Cout], residual (same layout as y), stats [B][Cout][2] int64 = (sum, sum of squares) of the result in
+ * 2^-24 fixed point, accumulated with integer atomics (must be zeroed by the caller). */
 int mdb_conv3d(const void* x, int batch, int cin, int z, int y_, int x_, const float* w, const float* bias, int cout,
-               int ksize, int stride, void* out, const float* rowbias, const void* residual, double* stats,
+               int ksize, int stride, void* out, const float* rowbias, const void* residual, long long* stats,
                int precision, void* stream);
-/* GroupNorm(32, eps=1e-6) [+ SiLU] from channel statistics: x [B][V][C], stats [B][C][2], y [B][V][C]. */
-int mdb_groupnorm_act(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int batch,
+/* GroupNorm(32, eps=1e-6) [+ SiLU] from channel statistics: x [B][V][C], stats [B][C][2] (fixed point, as above),
+ * y [B][V][C]. */
+int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma, const float* beta, void* y, int batch,
                       long long voxels, int channels, int silu, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -153,7 +153,7 @@ int mdb_sampler_run(mdb_unet* n, float* x, float* x_mean, const float* mask, con
 }
 
 int mdb_conv3d(const void* x, int B, int cin, int z, int y_, int x_, const float* w, const float* bias, int cout,
-               int ksize, int stride, void* out, const float* rowbias, const void* residual, double* stats,
+               int ksize, int stride, void* out, const float* rowbias, const void* residual, long long* stats,
                int precision, void* stream) {
   MDB_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
@@ -174,7 +174,7 @@ int mdb_conv3d(const void* x, int B, int cin, int z, int y_, int x_, const float
   MDB_API_END
 }
 
-int mdb_groupnorm_act(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int B,
+int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma, const float* beta, void* y, int B,
                       long long V, int C, int silu, int precision, void* stream) {
   MDB_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;

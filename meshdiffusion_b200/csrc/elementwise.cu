@@ -28,7 +28,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 
 // ------------------------------------------------------------------ GroupNorm finalize
 // nn.GroupNorm(32, C, eps=1e-6) statistics (layers.py:589,652,660; ddpm_res64.py:120): biased variance over
-// (C/32) channels x voxels. Channel sums arrive from the producing GEMM's epilogue in double precision.
+// (C/32) channels x voxels. Channel sums arrive from the producing GEMM's epilogue as 2^-24 fixed-point integers
+// (integer atomics commute, so the statistics -- and with them the whole forward pass -- are bitwise reproducible).
 __global__ void gn_finalize_kernel(GnFinalizeArgs a) {
   const int b = blockIdx.x;
   const int C = a.C0 + a.C1;
@@ -37,9 +38,9 @@ __global__ void gn_finalize_kernel(GnFinalizeArgs a) {
     double s = 0, ss = 0;
     for (int i = 0; i < cpg; ++i) {
       const int c = g * cpg + i;
-      const double* p = (c < a.C0) ? a.stats0 + ((long long)b * a.C0 + c) * 2
-                                   : a.stats1 + ((long long)b * a.C1 + (c - a.C0)) * 2;
-      s += p[0]; ss += p[1];
+      const long long* p = (c < a.C0) ? a.stats0 + ((long long)b * a.C0 + c) * 2
+                                      : a.stats1 + ((long long)b * a.C1 + (c - a.C0)) * 2;
+      s += (double)p[0] * (1.0 / 16777216.0); ss += (double)p[1] * (1.0 / 16777216.0);
     }
     const double n = a.count_per_channel * cpg;
     const double mean = s / n;
@@ -60,54 +61,89 @@ void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU), concat-aware
+// blockIdx.y = sample: its scale/shift vectors are staged in shared memory once; each thread keeps 4 independent
+// 16-byte loads in flight (grid-stride, unrolled) -- this is a pure HBM-bandwidth kernel.
 template <bool TF32>
-__global__ void norm_act_kernel(NormActArgs a, int B) {
+__global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a) {
   constexpr int VEC = TF32 ? 4 : 8;  // 16 bytes
+  constexpr int UNROLL = 4;
+  extern __shared__ float s_par[];
   const int C = a.C0 + a.C1;
   const int cv = C / VEC;
-  const long long total = (long long)B * a.voxels * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * VEC;
-    const long long bv = i / cv;
-    const int b = (int)(bv / a.voxels);
-    const float* sc = a.scale + (long long)b * C + c;
-    const float* sh = a.shift + (long long)b * C + c;
-    float v[VEC];
-    if (TF32) {
-      const float* src = (c < a.C0) ? (const float*)a.x0 + bv * a.ld0 + c : (const float*)a.x1 + bv * a.ld1 + (c - a.C0);
-      float4 t = __ldg((const float4*)src);
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-      const __nv_bfloat16* src = (c < a.C0) ? (const __nv_bfloat16*)a.x0 + bv * a.ld0 + c
-                                            : (const __nv_bfloat16*)a.x1 + bv * a.ld1 + (c - a.C0);
-      uint4 t = __ldg((const uint4*)src);
-      const __nv_bfloat162* h = (const __nv_bfloat162*)&t;
+  const int b = blockIdx.y;
+  float* s_sc = s_par;
+  float* s_sh = s_par + C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_sc[i] = a.scale[(long long)b * C + i];
+    s_sh[i] = a.shift[(long long)b * C + i];
+  }
+  __syncthreads();
+  const long long total = a.voxels * cv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long vbase = (long long)b * a.voxels;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNROLL) {
+    uint4 raw[UNROLL];
+    int cc[UNROLL];
+    long long vv[UNROLL];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        const int c = (int)(i % cv) * VEC;
+        const long long bv = vbase + i / cv;
+        cc[u] = c; vv[u] = bv;
+        const char* src;
+        if (TF32) src = (const char*)((c < a.C0) ? (const float*)a.x0 + bv * a.ld0 + c : (const float*)a.x1 + bv * a.ld1 + (c - a.C0));
+        else src = (const char*)((c < a.C0) ? (const __nv_bfloat16*)a.x0 + bv * a.ld0 + c : (const __nv_bfloat16*)a.x1 + bv * a.ld1 + (c - a.C0));
+        raw[u] = __ldg((const uint4*)src);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float y = v[j] * __ldg(sc + j) + __ldg(sh + j);
-      if (a.silu) y = silu_f(y);
-      v[j] = y;
-    }
-    if (TF32) {
-      float4 t = make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
-      *((float4*)((float*)a.y + bv * C + c)) = t;
-    } else {
-      uint4 t;
-      __nv_bfloat162* h = (__nv_bfloat162*)&t;
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total) continue;
+      const int c = cc[u];
+      float v[VEC];
+      if (TF32) {
+        const float* f = (const float*)&raw[u];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      *((uint4*)((__nv_bfloat16*)a.y + bv * C + c)) = t;
+        for (int j = 0; j < VEC; ++j) v[j] = f[j];
+      } else {
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[u];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float y = v[j] * s_sc[c + j] + s_sh[c + j];
+        if (a.silu) y = silu_f(y);
+        v[j] = y;
+      }
+      if (TF32) {
+        float4 t = make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
+        *((float4*)((float*)a.y + vv[u] * C + c)) = t;
+      } else {
+        uint4 t;
+        __nv_bfloat162* h = (__nv_bfloat162*)&t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *((uint4*)((__nv_bfloat16*)a.y + vv[u] * C + c)) = t;
+      }
     }
   }
 }
 void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s) {
   const int vec = a.tf32 ? 4 : 8;
-  const long long total = (long long)B * a.voxels * ((a.C0 + a.C1) / vec);
-  if (a.tf32) norm_act_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(a, B);
-  else norm_act_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(a, B);
+  const int C = a.C0 + a.C1;
+  const long long per_sample = a.voxels * (C / vec);
+  long long gx = (per_sample + 256 * 4 - 1) / (256 * 4);
+  const long long cap = (148LL * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)B);
+  const size_t smem = 2 * C * sizeof(float);
+  if (a.tf32) norm_act_kernel<true><<<grid, 256, smem, s>>>(a);
+  else norm_act_kernel<false><<<grid, 256, smem, s>>>(a);
   MDB_LAUNCH_CHECK();
 }
 
@@ -132,34 +168,69 @@ void launch_upsample2x(const void* x, void* y, int B, int Z, int Y, int X, int C
 }
 
 // ------------------------------------------------------------------ stem im2col
+// One block per (sample, z, y) row of the output: the k*k input rows it needs are staged in shared memory once,
+// then every thread emits 16-byte vectors of the [voxel][Kpad] operand matrix (column = cin*k^3 + tap).
 template <bool TF32>
-__global__ void im2col_kernel(const float* __restrict__ x, void* __restrict__ a, int B, int Cin, int R, int k, int Kpad) {
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, void* __restrict__ a, int Cin, int R, int k, int Kpad) {
+  constexpr int VEC = TF32 ? 4 : 8;
+  extern __shared__ float slab[];  // [Cin][k][k][R + 2*pad]
+  const int pad = k / 2, W = R + 2 * pad, T = k * k * k;
+  const int y0 = blockIdx.x % R, z0 = (blockIdx.x / R) % R, b = blockIdx.x / (R * R);
   const long long V = (long long)R * R * R;
-  const int T = k * k * k, pad = k / 2;
-  const long long total = (long long)B * V * Kpad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int col = (int)(i % Kpad);
-    long long r = i / Kpad;
-    const int xo = (int)(r % R); r /= R;
-    const int yo = (int)(r % R); r /= R;
-    const int zo = (int)(r % R); r /= R;
-    const int b = (int)r;
+  const int slab_n = Cin * k * k * W;
+  for (int i = threadIdx.x; i < slab_n; i += blockDim.x) {
+    int r = i;
+    const int xw = r % W; r /= W;
+    const int kh = r % k; r /= k;
+    const int kd = r % k; r /= k;
+    const int ci = r;
+    const int zi = z0 + kd - pad, yi = y0 + kh - pad, xi = xw - pad;
     float v = 0.f;
-    if (col < Cin * T) {
-      const int ci = col / T, tap = col % T;
-      const int kd = tap / (k * k), kh = (tap / k) % k, kw = tap % k;
-      const int zi = zo + kd - pad, yi = yo + kh - pad, xi = xo + kw - pad;
-      if (zi >= 0 && zi < R && yi >= 0 && yi < R && xi >= 0 && xi < R)
-        v = __ldg(x + ((long long)b * Cin + ci) * V + ((long long)zi * R + yi) * R + xi);
+    if (zi >= 0 && zi < R && yi >= 0 && yi < R && xi >= 0 && xi < R)
+      v = __ldg(x + ((long long)b * Cin + ci) * V + ((long long)zi * R + yi) * R + xi);
+    slab[i] = v;
+  }
+  __syncthreads();
+  const int kv = Kpad / VEC;
+  const long long row0 = (((long long)b * R + z0) * R + y0) * R;
+  for (int i = threadIdx.x; i < R * kv; i += blockDim.x) {
+    const int xo = i / kv, col0 = (i % kv) * VEC;
+    float v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int col = col0 + j;
+      float t = 0.f;
+      if (col < Cin * T) {
+        const int ci = col / T, tap = col % T;
+        const int kd = tap / (k * k), kh = (tap / k) % k, kw = tap % k;
+        t = slab[((ci * k + kd) * k + kh) * W + xo + kw];
+      }
+      v[j] = t;
     }
-    if (TF32) ((float*)a)[i] = round_tf32_rna(v);
-    else ((__nv_bfloat16*)a)[i] = __float2bfloat16(v);
+    if (TF32) {
+      *((float4*)((float*)a + (row0 + xo) * Kpad + col0)) =
+          make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
+    } else {
+      uint4 t;
+      __nv_bfloat162* h = (__nv_bfloat162*)&t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * Kpad + col0)) = t;
+    }
   }
 }
 void launch_im2col(const float* x, void* a, int B, int Cin, int R, int k, int Kpad, int tf32, cudaStream_t s) {
-  const long long total = (long long)B * R * R * R * Kpad;
-  if (tf32) im2col_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(x, a, B, Cin, R, k, Kpad);
-  else im2col_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(x, a, B, Cin, R, k, Kpad);
+  const size_t smem = (size_t)Cin * k * k * (R + 2 * (k / 2)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(im2col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(im2col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    configured = true;
+  }
+  if (smem > 100 * 1024) throw std::runtime_error("mdb: im2col slab too large");
+  const unsigned grid = (unsigned)(B * R * R);
+  if (tf32) im2col_kernel<true><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
+  else im2col_kernel<false><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
   MDB_LAUNCH_CHECK();
 }
 

@@ -9,8 +9,8 @@
 namespace mdb {
 
 struct GnFinalizeArgs {
-  const double* stats0; int C0;   // [B][C0][2]
-  const double* stats1; int C1;   // optional second (concatenated) source
+  const long long* stats0; int C0;   // [B][C0][2] (sum, sumsq) in 2^-24 fixed point
+  const long long* stats1; int C1;   // optional second (concatenated) source
   const float* gamma; const float* beta;
   float* scale; float* shift;     // [B][C0+C1]
   int groups; float eps; double count_per_channel;  // voxels per channel

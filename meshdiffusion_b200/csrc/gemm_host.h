@@ -88,7 +88,7 @@ class GemmOp {
   void set_rowbias(const float* rb, long long ld) { p.rowbias = rb; p.rowbias_ld = ld; }
   void set_out_col_stride(long long ocs) { p.ocs = ocs; }
   void set_residual(const void* res, long long ldr, long long batch_stride, bool fp32);
-  void set_stats(double* stats) { p.stats = stats; }
+  void set_stats(long long* stats) { p.stats = stats; }
   void set_alpha(float a) { p.alpha = a; }
 
   // Packs weights (device gather kernel), uploads the table, encodes the B map. Call after all add_* calls.

@@ -69,7 +69,7 @@ struct GemmParams {
   long long rsx, rsy, rsz, rsb;
   int res_fp32;
   float alpha;
-  double* stats;  // [Bn][N][2] (sum, sumsq) or null
+  long long* stats;  // [Bn][N][2] (sum, sumsq) in 2^-24 fixed point (order-independent accumulation) or null
 };
 
 template <int BLOCK_N>
@@ -78,7 +78,7 @@ struct GemmCfg {
   static constexpr int kSB = (BLOCK_N <= 128) ? 5 : 3;
   static constexpr int kBStageBytes = BLOCK_N * kRowBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int kStatsFloats = 4 * 2 * BLOCK_N;
+  static constexpr int kStatsFloats = 16 * BLOCK_N;  // [4 warps][sum,sumsq][N] column partials + 2 x [4 segs][N] bias
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kSA * kAStageBytes + kSB * kBStageBytes +
                                     kMaxLoads * 16 + kStatsFloats * 4 + (2 * kSA + 2 * kSB + 4) * 8 + 16;
 };
@@ -223,10 +223,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const long long ooff = xg * p.osx + yg * p.osy + zg * p.osz + bg * p.osb;
       const long long roff = xg * p.rsx + yg * p.rsy + zg * p.rsz + bg * p.rsb;
 
-      if (p.stats) {
-        for (int i = et; i < Cfg::kStatsFloats; i += 128) s_stats[i] = 0.f;
-        named_bar_sync(1, 128);
+      // stage bias + per-sample (time-embedding) bias of this tile's columns: s_bias[seg][col]
+      float* s_bias = s_stats + 8 * BLOCK_N + (it & 1) * 4 * BLOCK_N;  // double-buffered across tiles
+      for (int i = et; i < p.bb * BLOCK_N; i += 128) {
+        const int sg = i / BLOCK_N, c = i % BLOCK_N;
+        const int n = n0 + c, bgl = b0 + sg;
+        float bv = 0.f;
+        if (n < p.N) {
+          if (p.bias && !p.bias_on_m) bv += __ldg(p.bias + n);
+          if (p.rowbias && bgl < p.Bn) bv += __ldg(p.rowbias + static_cast<long long>(bgl) * p.rowbias_ld + n);
+        }
+        s_bias[i] = bv;
       }
+      named_bar_sync(1, 128);  // also orders the previous tile's statistics reads before this tile's writes
       mbar_wait(t_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
@@ -247,15 +256,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const bool full = (nb + 32 <= p.N) && (p.ocs == 1);
         float v[32];
         const float mbias = (p.bias && p.bias_on_m && valid) ? __ldg(p.bias + xg) : 0.f;
+        const float* sb = s_bias + (seg < 4 ? seg : 0) * BLOCK_N + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = __uint_as_float(rr[i]) * p.alpha + mbias;
-          if (full || nb + i < p.N) {
-            if (p.bias && !p.bias_on_m) a += __ldg(p.bias + nb + i);
-            if (p.rowbias && valid) a += __ldg(p.rowbias + static_cast<long long>(bg) * p.rowbias_ld + nb + i);
-          }
-          v[i] = a;
-        }
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) * p.alpha + mbias + sb[i];
         if (p.res && valid) {
           if (TF32 || p.res_fp32) {
             const float* rp = reinterpret_cast<const float*>(p.res) + roff + nb;
@@ -334,24 +337,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
             }
           }
-          if (seg < 4) {
-            atomicAdd(&s_stats[(seg * 2 + 0) * BLOCK_N + ch * 32 + lane], s[0]);
-            atomicAdd(&s_stats[(seg * 2 + 1) * BLOCK_N + ch * 32 + lane], ss[0]);
-          }
+          // per-warp slot, no atomics: the cross-warp sum below runs in a fixed order (deterministic results)
+          s_stats[(q * 2 + 0) * BLOCK_N + ch * 32 + lane] = s[0];
+          s_stats[(q * 2 + 1) * BLOCK_N + ch * 32 + lane] = ss[0];
         }
       }
       if (p.stats) {
         named_bar_sync(1, 128);
+        const int warps_per_seg = rows_per_b >= 128 ? 4 : rows_per_b / 32;
         for (int i = et; i < p.bb * BLOCK_N; i += 128) {
           const int sg = i / BLOCK_N, c = i % BLOCK_N;
           const int bgl = b0 + sg, n = n0 + c;
           if (bgl < p.Bn && n < p.N) {
-            double* dst = p.stats + (static_cast<long long>(bgl) * p.N + n) * 2;
-            atomicAdd(dst, static_cast<double>(s_stats[(sg * 2 + 0) * BLOCK_N + c]));
-            atomicAdd(dst + 1, static_cast<double>(s_stats[(sg * 2 + 1) * BLOCK_N + c]));
+            float ts = 0.f, tq = 0.f;
+            for (int w = sg * warps_per_seg; w < (sg + 1) * warps_per_seg; ++w) {
+              ts += s_stats[(w * 2 + 0) * BLOCK_N + c];
+              tq += s_stats[(w * 2 + 1) * BLOCK_N + c];
+            }
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.stats) + (static_cast<long long>(bgl) * p.N + n) * 2;
+            atomicAdd(dst, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(ts) * 16777216.0)));
+            atomicAdd(dst + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(tq) * 16777216.0)));
           }
         }
-        named_bar_sync(1, 128);
       }
     }
   }

@@ -481,7 +481,7 @@ UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(cfg.precisio
   arena_bytes_ = arena_.peak();
   if (dry_only) return;
   arena_base_ = (char*)dmalloc(arena_bytes_, false);
-  stats_base_ = (double*)dmalloc(stats_doubles_ * sizeof(double));
+  stats_base_ = (long long*)dmalloc(stats_doubles_ * sizeof(long long));
   const int tdim = 4 * cfg_.nf;
   temb_act_ = (float*)dmalloc((size_t)cfg_.max_batch * tdim * 4);
   dense_w_ = (float*)dmalloc((size_t)dense_total_ * tdim * 4);
@@ -530,7 +530,7 @@ void UNet::forward(const float* x, const float* labels, float* out, int B, cudaS
   if (!committed_) throw std::runtime_error("mdb: parameters changed, call commit() before forward()");
   if (B < 1 || B > cfg_.max_batch) throw std::runtime_error("mdb: batch out of range");
   rt_x_ = x; rt_labels_ = labels; rt_out_ = out;
-  MDB_CUDA_CHECK(cudaMemsetAsync(stats_base_, 0, stats_doubles_ * sizeof(double), s));
+  MDB_CUDA_CHECK(cudaMemsetAsync(stats_base_, 0, stats_doubles_ * sizeof(long long), s));
   for (auto& st : steps_) st.fn(s, B);
 }
 
@@ -540,7 +540,7 @@ std::vector<std::pair<std::string, float>> UNet::profile(const float* x, const f
   std::vector<std::pair<std::string, float>> res;
   std::vector<cudaEvent_t> ev(steps_.size() + 1);
   for (auto& e : ev) MDB_CUDA_CHECK(cudaEventCreate(&e));
-  MDB_CUDA_CHECK(cudaMemsetAsync(stats_base_, 0, stats_doubles_ * sizeof(double), s));
+  MDB_CUDA_CHECK(cudaMemsetAsync(stats_base_, 0, stats_doubles_ * sizeof(long long), s));
   MDB_CUDA_CHECK(cudaEventRecord(ev[0], s));
   for (size_t i = 0; i < steps_.size(); ++i) {
     steps_[i].fn(s, B);

@@ -51,7 +51,7 @@ class Arena {
 struct Tens {
   size_t off = 0, bytes = 0;
   int C = 0, R = 0;
-  double* stats = nullptr;
+  long long* stats = nullptr;
   void* ptr = nullptr;
 };
 typedef std::shared_ptr<Tens> TensP;
@@ -87,7 +87,7 @@ class UNet {
   Arena arena_;
   char* arena_base_ = nullptr;
   size_t arena_bytes_ = 0;
-  double* stats_base_ = nullptr;
+  long long* stats_base_ = nullptr;
   size_t stats_doubles_ = 0, stats_cursor_ = 0;
   std::vector<std::unique_ptr<GemmOp>> gemms_;
   std::vector<std::unique_ptr<GemmOp>> commit_gemms_;

@@ -33,7 +33,7 @@ def conv3d(x, weight, bias=None, stride=1, rowbias=None, residual=None, want_sta
     Cout, k = weight.shape[0], weight.shape[2]
     w = weight.detach().float().contiguous()
     y = torch.empty((B, Z // stride, Y // stride, X // stride, Cout), device=x.device, dtype=x.dtype)
-    stats = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.float64) if want_stats else None
+    stats = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.int64) if want_stats else None
     b = bias.detach().float().contiguous() if bias is not None else None
     rb = rowbias.detach().float().contiguous() if rowbias is not None else None
     if residual is not None:
@@ -41,7 +41,8 @@ def conv3d(x, weight, bias=None, stride=1, rowbias=None, residual=None, want_sta
     _native.check(L.mdb_conv3d(_native.ptr(x), B, Cin, Z, Y, X, _native.ptr(w), _native.ptr(b), Cout, k, stride,
                                _native.ptr(y), _native.ptr(rb), _native.ptr(residual), _native.ptr(stats),
                                PRECISIONS[precision], _native.current_stream()))
-    return (y, stats) if want_stats else y
+    # statistics are 2^-24 fixed-point integers inside the library; return them as float64 sums
+    return (y, stats.double() / 16777216.0) if want_stats else y
 
 
 def groupnorm_act(x, stats, gamma, beta, silu=True, precision="bf16"):
@@ -50,6 +51,7 @@ def groupnorm_act(x, stats, gamma, beta, silu=True, precision="bf16"):
     B, C = x.shape[0], x.shape[-1]
     V = x.numel() // (B * C)
     y = torch.empty_like(x)
+    stats = torch.round(stats.double() * 16777216.0).to(torch.int64).contiguous()
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
     _native.check(L.mdb_groupnorm_act(_native.ptr(x), _native.ptr(stats), _native.ptr(g), _native.ptr(bt), _native.ptr(y),
