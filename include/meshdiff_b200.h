@@ -62,6 +62,11 @@ int mdb_unet_info(mdb_unet* net, double* flops_per_sample, long long* arena_byte
 int mdb_unet_profile(mdb_unet* net, const float* x, const float* labels, float* out, int batch, void* stream,
                      char* names_buf, int names_len, float* ms, int max_steps, int* n_steps);
 
+/* Position-weighted 64-bit fingerprints of n fp32 device tensors (ptrs_dev / numels_dev / out_dev are device
+ * arrays of n entries). Host plumbing for load_state_dict-style change detection; no reference counterpart. */
+int mdb_fingerprint(const void* const* ptrs_dev, const long long* numels_dev, int n, unsigned long long* out_dev,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Sampler. Replaces AncestralSamplingPredictor.vpsde_update_fn + get_score_fn + the two grid_mask multiplies of
  * pc_sampler (lib/diffusion/sampling.py:222-230, 469-478; lib/diffusion/models/utils.py:191-198).

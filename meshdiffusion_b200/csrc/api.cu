@@ -129,6 +129,29 @@ int mdb_sampler_update(const float* eps, float* x, float* x_mean, const float* n
   MDB_API_END
 }
 
+// Order-independent 64-bit fingerprint of fp32 tensors (position-weighted sum of the raw words, integer atomics).
+// The Python shell uses it to notice parameter edits that bypass autograd's version counters (`p.data[...] = ...`,
+// which is how the reference's trainer writes the grid mask and how its EMA copies weights).
+__global__ void fingerprint_kernel(const unsigned int* const* ptrs, const long long* numels, unsigned long long* out) {
+  const int t = blockIdx.y;
+  const unsigned int* p = ptrs[t];
+  const long long n = numels[t];
+  unsigned long long h = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    h += (unsigned long long)p[i] * (0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1) | 1ull);
+  for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0 && h) atomicAdd(out + t, h);
+}
+
+int mdb_fingerprint(const void* const* ptrs_dev, const long long* numels_dev, int n, unsigned long long* out_dev, void* stream) {
+  MDB_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  MDB_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, (size_t)n * 8, s));
+  fingerprint_kernel<<<dim3(64, n), 256, 0, s>>>(reinterpret_cast<const unsigned int* const*>(ptrs_dev), numels_dev, out_dev);
+  MDB_CUDA_CHECK(cudaGetLastError());
+  MDB_API_END
+}
+
 __global__ void fill_kernel(float* p, float v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -292,6 +292,36 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   MDB_CUDA_CHECK(cudaMemcpyAsync(d_loads, loads.data(), loads.size() * sizeof(LoadEntry), cudaMemcpyHostToDevice, stream));
   p.loads = d_loads;
   p.n_loads = (int)loads.size();
+  // pipeline segments: runs of identical entries; plain (nk == 1) entries are paired two per stage
+  {
+    const int btile = block_n * kRowBytes;
+    const int stage_bytes = kAStageBytes + 3 * 128 * kRowBytes;
+    p.n_segs = 0;
+    auto push = [&](int n_groups, int epg, const LoadEntry& e) {
+      if (n_groups <= 0) return;
+      if (p.n_segs >= kMaxSegs) throw std::runtime_error("mdb: too many pipeline segments");
+      GemmSeg sg{};
+      sg.n_groups = n_groups; sg.epg = epg; sg.nk = e.nk;
+      sg.a_bytes = e.rows * kRowBytes;
+      sg.a_stride = (sg.a_bytes + 1023) / 1024 * 1024;
+      sg.jbytes = e.jrows * kRowBytes;
+      if (epg * (sg.a_stride + e.nk * btile) > stage_bytes) throw std::runtime_error("mdb: pipeline group exceeds the stage size");
+      p.segs[p.n_segs++] = sg;
+    };
+    size_t i = 0;
+    while (i < loads.size()) {
+      size_t j = i;
+      while (j < loads.size() && loads[j].nk == loads[i].nk && loads[j].rows == loads[i].rows && loads[j].jrows == loads[i].jrows) ++j;
+      const int run = (int)(j - i);
+      if (loads[i].nk == 1 && 2 * (loads[i].rows * kRowBytes + btile) <= stage_bytes) {
+        push(run / 2, 2, loads[i]);
+        push(run % 2, 1, loads[i]);
+      } else {
+        push(run, 1, loads[i]);
+      }
+      i = j;
+    }
+  }
   if (!b_from_act) {
     const long long ktot = 1LL * ksteps * kb_elems(prec);
     const long long bytes = ktot * p.N * esize(prec);

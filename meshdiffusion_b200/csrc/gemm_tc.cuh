@@ -25,7 +25,7 @@ constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;                       // bytes of K per row per k-step (one 128B swizzle atom)
 constexpr int kAStageRows = 160;                     // 128 + up to 32 halo rows (5-tap reuse)
 constexpr int kAStageBytes = kAStageRows * kRowBytes;  // 20480, multiple of 1024
-constexpr int kMaxLoads = 1024;
+constexpr int kMaxLoads = 2048;
 constexpr int kMaxAMaps = 10;
 constexpr int kGemmThreads = 256;
 
@@ -44,11 +44,26 @@ struct __align__(16) LoadEntry {
 };
 static_assert(sizeof(LoadEntry) == 16, "LoadEntry must be 16 bytes");
 
+// A run of identical pipeline groups. One group = one shared-memory stage = one full/empty mbarrier pair:
+// `epg` A boxes (1 halo box, or 2 plain boxes) and the epg*nk weight tiles they are multiplied with. All fields are
+// warp-uniform kernel parameters, so the MMA warp's control flow and descriptor arithmetic never touch memory.
+struct GemmSeg {
+  int n_groups;
+  int epg;       // load-table entries (A boxes) per group
+  int nk;        // k-steps per entry
+  int a_bytes;   // bytes of one A box (rows * 128) -- the TMA transaction size
+  int a_stride;  // distance between the group's A boxes in the stage (multiple of 1024)
+  int jbytes;    // A-descriptor advance between the k-steps of one entry (halo reuse)
+};
+constexpr int kMaxSegs = 8;
+
 struct GemmParams {
   CUtensorMap amap[kMaxAMaps];
   CUtensorMap bmap;
   const LoadEntry* loads;
   int n_loads;
+  int n_segs;
+  GemmSeg segs[kMaxSegs];
   int bx, by, bz, bb;  // M-tile box (product 128)
   int X, Y, Z, Bn;     // output extents
   int tx, ty, tz, tb;  // tile counts per axis
@@ -74,31 +89,50 @@ struct GemmParams {
 
 template <int BLOCK_N>
 struct GemmCfg {
-  static constexpr int kSA = 3;
-  static constexpr int kSB = (BLOCK_N <= 128) ? 5 : 3;
-  static constexpr int kBStageBytes = BLOCK_N * kRowBytes;
+  static constexpr int kStages = 3;
+  static constexpr int kBTileBytes = BLOCK_N * kRowBytes;
+  // a stage holds one halo box + 3 weight tiles of 128 rows (68 KB), or 2 plain boxes + 2 tiles (64 KB)
+  static constexpr int kStageBytes = kAStageBytes + 3 * 128 * kRowBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int kStatsFloats = 16 * BLOCK_N;  // [4 warps][sum,sumsq][N] column partials + 2 x [4 segs][N] bias
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kSA * kAStageBytes + kSB * kBStageBytes +
-                                    kMaxLoads * 16 + kStatsFloats * 4 + (2 * kSA + 2 * kSB + 4) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatsFloats * 4 +
+                                    (2 * kStages + 4) * 8 + 16;
 };
+
+// D[tmem] (+)= A * B with descriptors given as their low 32 bits (start address >> 4 | LBO) and a shared constant high
+// word (SBO = 1024 B, version 1, SWIZZLE_128B): all descriptor arithmetic is 32-bit adds on uniform values.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <bool TF32>
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+  }
+}
 
 template <int BLOCK_N, bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
+  constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + SA * kAStageBytes;
-  LoadEntry* s_loads = reinterpret_cast<LoadEntry*>(smem_b + SB * Cfg::kBStageBytes);
-  float* s_stats = reinterpret_cast<float*>(s_loads + kMaxLoads);
+  float* s_stats = reinterpret_cast<float*>(smem + NS * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + Cfg::kStatsFloats);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
 
-  const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA;
-  const uint32_t b_full = a_empty + 8 * SA, b_empty = b_full + 8 * SB;
-  const uint32_t t_full = b_empty + 8 * SB, t_empty = t_full + 16;
+  const uint32_t stage0 = smem_u32(smem);
+  const uint32_t full = smem_u32(bars), empty = full + 8 * NS;
+  const uint32_t t_full = empty + 8 * NS, t_empty = t_full + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -107,14 +141,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     tma_prefetch_desc(&p.bmap);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(s_tmem));
-  for (int i = threadIdx.x; i < p.n_loads; i += kGemmThreads) s_loads[i] = p.loads[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -134,37 +166,46 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    uint32_t st = 0, ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int x0, y0, z0, b0, n0;
       decode(tile, x0, y0, z0, b0, n0);
-      int kcol = 0;
+      int kcol = 0, l = 0;
       const int bcoord = p.b_batched ? b0 : 0;
-      for (int l = 0; l < p.n_loads; ++l) {
-        const LoadEntry e = s_loads[l];
-        mbar_wait(a_empty + 8 * sa, pa ^ 1);
-        if (lane == 0) {
-          mbar_expect_tx(a_full + 8 * sa, static_cast<uint32_t>(e.rows) * kRowBytes);
-          tma_load_5d(&p.amap[e.tmap], a_full + 8 * sa, smem_u32(smem_a + sa * kAStageBytes), e.c0, x0 + e.dx,
-                      y0 + e.dy, z0 + e.dz, b0);
-        }
-        for (int j = 0; j < e.nk; ++j) {
-          mbar_wait(b_empty + 8 * sb, pb ^ 1);
+      for (int sg = 0; sg < p.n_segs; ++sg) {
+        const GemmSeg seg = p.segs[sg];
+        const uint32_t group_bytes = seg.epg * (seg.a_bytes + seg.nk * Cfg::kBTileBytes);
+        const uint32_t b_base = seg.epg * seg.a_stride;
+        for (int g = 0; g < seg.n_groups; ++g) {
+          // the table entries of this group are fetched before blocking on the stage
+          const uint4 raw0 = __ldg(reinterpret_cast<const uint4*>(p.loads + l));
+          uint4 raw1 = raw0;
+          if (seg.epg > 1) raw1 = __ldg(reinterpret_cast<const uint4*>(p.loads + l + 1));
+          mbar_wait(empty + 8 * st, ph ^ 1);
           if (lane == 0) {
-            mbar_expect_tx(b_full + 8 * sb, Cfg::kBStageBytes);
-            tma_load_3d(&p.bmap, b_full + 8 * sb, smem_u32(smem_b + sb * Cfg::kBStageBytes), kcol, n0, bcoord);
+            const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
+            const uint32_t bar = full + 8 * st;
+            mbar_expect_tx(bar, group_bytes);
+            for (int e = 0; e < seg.epg; ++e) {
+              const uint4 raw = e == 0 ? raw0 : raw1;
+              const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
+              tma_load_5d(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
+              for (int j = 0; j < seg.nk; ++j) {
+                tma_load_3d(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kcol, n0, bcoord);
+                kcol += p.kb_elems;
+              }
+            }
           }
-          kcol += p.kb_elems;
-          if (++sb == SB) { sb = 0; pb ^= 1; }
+          kcol = __shfl_sync(0xffffffffu, kcol, 0);
+          l += seg.epg;
+          if (++st == NS) { st = 0; ph ^= 1; }
         }
-        if (++sa == SA) { sa = 0; pa ^= 1; }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc(TF32, kBlockM, BLOCK_N);
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    uint32_t st = 0, ph = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -173,30 +214,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       uint32_t accumulate = 0;
-      for (int l = 0; l < p.n_loads; ++l) {
-        const LoadEntry e = s_loads[l];
-        mbar_wait(a_full + 8 * sa, pa);
-        const uint32_t a_base = smem_u32(smem_a + sa * kAStageBytes);
-        for (int j = 0; j < e.nk; ++j) {
-          mbar_wait(b_full + 8 * sb, pb);
+      for (int sg = 0; sg < p.n_segs; ++sg) {
+        const GemmSeg seg = p.segs[sg];
+        const uint32_t b_base = seg.epg * seg.a_stride;
+        for (int g = 0; g < seg.n_groups; ++g) {
+          mbar_wait(full + 8 * st, ph);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_addr = a_base + j * e.jrows * kRowBytes;
-            const uint32_t b_addr = smem_u32(smem_b + sb * Cfg::kBStageBytes);
+            const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
+            for (int e = 0; e < seg.epg; ++e) {
+              for (int j = 0; j < seg.nk; ++j) {
+                const uint32_t a_lo = desc_lo(sbase + e * seg.a_stride + j * seg.jbytes);
+                const uint32_t b_lo = desc_lo(sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes);
 #pragma unroll
-            for (int k = 0; k < kRowBytes / 32; ++k) {
-              umma_ss<TF32>(d_tmem, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32),
-                            idesc, accumulate);
-              accumulate = 1;
+                for (int k = 0; k < kRowBytes / 32; ++k) {
+                  umma_lo<TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
             }
-            umma_commit(b_empty + 8 * sb);
+            umma_commit(empty + 8 * st);
           }
           __syncwarp();
-          if (++sb == SB) { sb = 0; pb ^= 1; }
+          if (++st == NS) { st = 0; ph ^= 1; }
         }
-        if (lane == 0) umma_commit(a_empty + 8 * sa);
-        __syncwarp();
-        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
       if (lane == 0) umma_commit(t_full + 8 * acc);
       __syncwarp();

@@ -166,23 +166,57 @@ class ScoreNet(nn.Module):
         except Exception:
             pass
 
-    def sync_parameters(self, force=False):
-        """Pushes changed master parameters into the engine and re-derives packed weights / the stem field."""
+    def _fingerprints(self):
+        """One kernel over all master parameters -> int64 fingerprints on the host (synchronises)."""
         L = _native.lib()
-        versions = [(self._param(n).data_ptr(), self._param(n)._version) for n in self._names]
-        if not force and versions == self._synced:
+        params = [self._param(n) for n in self._names]
+        key = tuple(p.data_ptr() for p in params)
+        if getattr(self, "_fp_key", None) != key:
+            dev = params[0].device
+            self._fp_ptrs = torch.tensor(key, dtype=torch.int64, device=dev)
+            self._fp_numels = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
+            self._fp_out = torch.empty(len(params), dtype=torch.int64, device=dev)
+            self._fp_key = key
+        _native.check(L.mdb_fingerprint(_native.ptr(self._fp_ptrs), _native.ptr(self._fp_numels), len(params),
+                                        _native.ptr(self._fp_out), _native.current_stream()))
+        return self._fp_out.cpu()
+
+    def frozen(self):
+        """Context manager: the caller promises not to touch the parameters inside (e.g. the sampler loop), so the
+        per-call change detection (a 1.5 GB read + a host sync) is skipped."""
+        net = self
+
+        class _Frozen:
+            def __enter__(self_inner):
+                net.sync_parameters()
+                net._frozen = True
+
+            def __exit__(self_inner, *exc):
+                net._frozen = False
+
+        return _Frozen()
+
+    def sync_parameters(self, force=False):
+        """Pushes changed master parameters into the engine and re-derives packed weights / the stem field.
+        Changes are detected by content fingerprints, because `p.data[...] = v` (how trainer.py:61-63 writes the mask
+        and ema.py copies weights) does not bump autograd's version counters."""
+        L = _native.lib()
+        if getattr(self, "_frozen", False) and not force:
+            return
+        fp = self._fingerprints()
+        changed = None if (force or self._synced is None) else (fp != self._synced).nonzero().flatten().tolist()
+        if changed is not None and not changed:
             return
         stream = _native.current_stream()
         for i, n in enumerate(self._names):
-            if not force and self._synced is not None and versions[i] == self._synced[i]:
+            if changed is not None and i not in changed:
                 continue
-            p = self._param(n).detach()
-            src = p.float().contiguous()
+            src = self._param(n).detach().float().contiguous()
             _native.check(L.mdb_unet_set_param(self._handle, n.encode(), _native.ptr(src), src.numel(),
                                                1 if src.is_cuda else 0, stream))
         torch.cuda.current_stream().synchronize()
         _native.check(L.mdb_unet_commit(self._handle, stream))
-        self._synced = versions
+        self._synced = fp
 
     def forward(self, x, labels):
         if not x.is_cuda:

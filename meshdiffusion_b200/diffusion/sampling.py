@@ -257,6 +257,10 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
                 assert mask_flat.numel() == x[0, 0].numel()
                 x = x.contiguous()
             traj = []
+            if use_fused:
+                net._ensure_engine(B, x.device)
+                net.sync_parameters()
+                net._frozen = True  # nobody edits the weights inside the loop: skip per-step change detection
 
             def step(x, i):
                 vec_t = torch.ones(B, device=device) * timesteps[i]
@@ -296,6 +300,8 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
                         x, x_mean = step(x, i)
                         if return_traj and i >= 700 and i % 10 == 0:
                             traj.append(compute_xzero(model, x, timesteps[i], grid_mask))
+            if use_fused:
+                net._frozen = False
             if return_traj:
                 return traj, sde.N * (n_steps + 1)
             return inverse_scaler(x_mean if denoise else x), sde.N * (n_steps + 1)
