@@ -25,6 +25,14 @@ __device__ __forceinline__ float round_tf32_rna(float x) {
   return __uint_as_float(u);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// x*sigmoid(x) = 0.5x(1 + tanh(x/2)) with the single-MUFU tanh.approx (rel. error 2^-11: below bf16 resolution);
+// halves the MUFU pressure of the bf16 GroupNorm+SiLU pass, which otherwise co-limits with HBM bandwidth.
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
 
 // ------------------------------------------------------------------ GroupNorm finalize
 // nn.GroupNorm(32, C, eps=1e-6) statistics (layers.py:589,652,660; ddpm_res64.py:120): biased variance over
@@ -78,19 +86,21 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a) {
     s_sh[i] = a.shift[(long long)b * C + i];
   }
   __syncthreads();
-  const long long total = a.voxels * cv;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  // per-sample index space fits 32 bits (voxels * C/VEC <= 2^31): keep the div/mod 32-bit
+  const unsigned total = (unsigned)(a.voxels * cv);
+  const unsigned stride = gridDim.x * blockDim.x;
   const long long vbase = (long long)b * a.voxels;
-  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNROLL) {
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNROLL) {
     uint4 raw[UNROLL];
     int cc[UNROLL];
     long long vv[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const long long i = i0 + u * stride;
+      const unsigned i = i0 + u * stride;
       if (i < total) {
-        const int c = (int)(i % cv) * VEC;
-        const long long bv = vbase + i / cv;
+        const unsigned vox = i / (unsigned)cv;
+        const int c = (int)(i - vox * (unsigned)cv) * VEC;
+        const long long bv = vbase + vox;
         cc[u] = c; vv[u] = bv;
         const char* src;
         if (TF32) src = (const char*)((c < a.C0) ? (const float*)a.x0 + bv * a.ld0 + c : (const float*)a.x1 + bv * a.ld1 + (c - a.C0));
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a) {
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const long long i = i0 + u * stride;
+      const unsigned i = i0 + u * stride;
       if (i >= total) continue;
       const int c = cc[u];
       float v[VEC];
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         float y = v[j] * s_sc[c + j] + s_sh[c + j];
-        if (a.silu) y = silu_f(y);
+        if (a.silu) y = TF32 ? silu_f(y) : silu_fast(y);
         v[j] = y;
       }
       if (TF32) {
@@ -190,22 +200,27 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
       v = __ldg(x + ((long long)b * Cin + ci) * V + ((long long)zi * R + yi) * R + xi);
     slab[i] = v;
   }
+  // slab offset of every operand column (independent of x): removes all div/mod from the emit loop
+  int* coloff = reinterpret_cast<int*>(slab + slab_n);
+  for (int col = threadIdx.x; col < Kpad; col += blockDim.x) {
+    int off = -1;
+    if (col < Cin * T) {
+      const int ci = col / T, tap = col % T;
+      const int kd = tap / (k * k), kh = (tap / k) % k, kw = tap % k;
+      off = ((ci * k + kd) * k + kh) * W + kw;
+    }
+    coloff[col] = off;
+  }
   __syncthreads();
   const int kv = Kpad / VEC;
   const long long row0 = (((long long)b * R + z0) * R + y0) * R;
   for (int i = threadIdx.x; i < R * kv; i += blockDim.x) {
-    const int xo = i / kv, col0 = (i % kv) * VEC;
+    const int xo = i / kv, col0 = (i - xo * kv) * VEC;
     float v[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const int col = col0 + j;
-      float t = 0.f;
-      if (col < Cin * T) {
-        const int ci = col / T, tap = col % T;
-        const int kd = tap / (k * k), kh = (tap / k) % k, kw = tap % k;
-        t = slab[((ci * k + kd) * k + kh) * W + xo + kw];
-      }
-      v[j] = t;
+      const int off = coloff[col0 + j];
+      v[j] = off >= 0 ? slab[off + xo] : 0.f;
     }
     if (TF32) {
       *((float4*)((float*)a + (row0 + xo) * Kpad + col0)) =
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
   }
 }
 void launch_im2col(const float* x, void* a, int B, int Cin, int R, int k, int Kpad, int tf32, cudaStream_t s) {
-  const size_t smem = (size_t)Cin * k * k * (R + 2 * (k / 2)) * sizeof(float);
+  const size_t smem = (size_t)Cin * k * k * (R + 2 * (k / 2)) * sizeof(float) + (size_t)Kpad * sizeof(int);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(im2col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -240,10 +255,14 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L
   __shared__ float red[32];
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     float* p = s + row * L;
-    float vals[16];  // L <= 16 * blockDim.x
-    int n = 0;
+    float vals[16];  // L <= 16 * blockDim.x; fully unrolled so the array stays in registers
     float m = -INFINITY;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) { vals[n] = p[i]; m = fmaxf(m, vals[n]); ++n; }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = threadIdx.x + j * 256;
+      vals[j] = i < L ? p[i] : -INFINITY;
+      m = fmaxf(m, vals[j]);
+    }
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
     __syncthreads();
@@ -251,7 +270,8 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
     __syncthreads();
     float sum = 0.f;
-    for (int j = 0; j < n; ++j) { vals[j] = __expf(vals[j] - m); sum += vals[j]; }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { vals[j] = __expf(vals[j] - m); sum += vals[j]; }
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
     __syncthreads();
@@ -259,10 +279,13 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
     const float inv = 1.f / sum;
     __syncthreads();  // every thread has consumed its fp32 logits before anyone overwrites the row
-    n = 0;
-    for (int i = threadIdx.x; i < L; i += blockDim.x, ++n) {
-      if (TF32) p[i] = round_tf32_rna(vals[n] * inv);
-      else ((__nv_bfloat16*)p)[i] = __float2bfloat16(vals[n] * inv);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = threadIdx.x + j * 256;
+      if (i < L) {
+        if (TF32) p[i] = round_tf32_rna(vals[j] * inv);
+        else ((__nv_bfloat16*)p)[i] = __float2bfloat16(vals[j] * inv);
+      }
     }
   }
 }

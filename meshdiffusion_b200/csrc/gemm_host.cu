@@ -1,6 +1,7 @@
 // Host-side builders for the tcgen05 implicit-GEMM kernel (see gemm_tc.cuh).
 #include "gemm_host.h"
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 namespace mdb {
@@ -89,6 +90,10 @@ void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N,
   p.out = out;
   p.osx = osx; p.osy = osy; p.osz = osz; p.osb = osb;
   p.out_fp32 = out_fp32 ? 1 : 0;
+  {
+    const char* e = getenv("MDB_TF32_ROUND_STORE");
+    p.round_out = (prec == kTF32 && !out_fp32 && e && e[0] == '1') ? 1 : 0;
+  }
   p.alpha = 1.f;
   p.ocs = 1;
   p.kb_elems = kb_elems(prec);

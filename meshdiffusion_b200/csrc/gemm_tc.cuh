@@ -76,6 +76,7 @@ struct GemmParams {
   long long osx, osy, osz, osb;  // output element strides per voxel axis
   long long ocs;                 // output column stride (1 = channels contiguous; else scalar store path)
   int out_fp32;
+  int round_out;  // TF32 operands: round stored activations to tf32 (rna) so downstream MMAs do not truncate them
   const float* bias;
   int bias_on_m;
   const float* rowbias;  // [Bn][rowbias_ld] per-sample bias (time embedding projection) or null
@@ -93,7 +94,9 @@ struct GemmCfg {
   static constexpr int kBTileBytes = BLOCK_N * kRowBytes;
   // a stage holds one halo box + 3 weight tiles of 128 rows (68 KB), or 2 plain boxes + 2 tiles (64 KB)
   static constexpr int kStageBytes = kAStageBytes + 3 * 128 * kRowBytes;
-  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  // The whole TMEM (512 columns) is taken: with one CTA per SM the allocation then always starts at column 0, so
+  // accumulator addresses are compile-time/uniform values and the MMA issue loop needs no per-instruction R2UR.
+  static constexpr int kTmemCols = 512;
   static constexpr int kStatsFloats = 16 * BLOCK_N;  // [4 warps][sum,sumsq][N] column partials + 2 x [4 segs][N] bias
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatsFloats * 4 +
                                     (2 * kStages + 4) * 8 + 16;
@@ -150,7 +153,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = 0;
+  if (*s_tmem != 0) {
+    if (threadIdx.x == 0) printf("mdb: unexpected TMEM base %u\n", *s_tmem);
+    __trap();
+  }
 
   const int tiles_m = p.tx * p.ty * p.tz * p.tb;
   const int total_tiles = tiles_m * p.n_tiles_n;
@@ -182,21 +189,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           uint4 raw1 = raw0;
           if (seg.epg > 1) raw1 = __ldg(reinterpret_cast<const uint4*>(p.loads + l + 1));
           mbar_wait(empty + 8 * st, ph ^ 1);
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
             const uint32_t bar = full + 8 * st;
             mbar_expect_tx(bar, group_bytes);
+            int kc = kcol;
             for (int e = 0; e < seg.epg; ++e) {
               const uint4 raw = e == 0 ? raw0 : raw1;
               const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
               tma_load_5d(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
               for (int j = 0; j < seg.nk; ++j) {
-                tma_load_3d(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kcol, n0, bcoord);
-                kcol += p.kb_elems;
+                tma_load_3d(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, n0, bcoord);
+                kc += p.kb_elems;
               }
             }
           }
-          kcol = __shfl_sync(0xffffffffu, kcol, 0);
+          __syncwarp();
+          kcol += seg.epg * seg.nk * p.kb_elems;
           l += seg.epg;
           if (++st == NS) { st = 0; ph ^= 1; }
         }
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         for (int g = 0; g < seg.n_groups; ++g) {
           mbar_wait(full + 8 * st, ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
             for (int e = 0; e < seg.epg; ++e) {
               for (int j = 0; j < seg.nk; ++j) {
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (++st == NS) { st = 0; ph ^= 1; }
         }
       }
-      if (lane == 0) umma_commit(t_full + 8 * acc);
+      if (elect_one()) umma_commit(t_full + 8 * acc);
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -335,8 +344,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             float* op = reinterpret_cast<float*>(p.out) + ooff + nb;
             if (full) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(op)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              for (int i = 0; i < 8; ++i) {
+                float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if (p.round_out) { t.x = to_tf32_rna(t.x); t.y = to_tf32_rna(t.y); t.z = to_tf32_rna(t.z); t.w = to_tf32_rna(t.w); }
+                reinterpret_cast<float4*>(op)[i] = t;
+              }
             } else {
               for (int i = 0; i < 32; ++i) if (nb + i < p.N) op[i * p.ocs] = v[i];
             }
