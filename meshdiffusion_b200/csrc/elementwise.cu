@@ -69,75 +69,68 @@ void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU), concat-aware
-// blockIdx.y = sample: its scale/shift vectors are staged in shared memory once; each thread keeps 4 independent
-// 16-byte loads in flight (grid-stride, unrolled) -- this is a pure HBM-bandwidth kernel.
+// blockIdx.y = sample. Every thread owns ONE 16-byte channel vector for the whole kernel (block = k voxels x C/VEC
+// vectors): its scale/shift live in registers, its source pointer is selected once, and the loop body is
+// load -> fma -> silu -> store with 4 voxels in flight. No div/mod or table lookups in the loop: the kernel is
+// HBM-bound instead of issue-bound.
 template <bool TF32>
-__global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a) {
+__global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, int k) {
   constexpr int VEC = TF32 ? 4 : 8;  // 16 bytes
   constexpr int UNROLL = 4;
-  extern __shared__ float s_par[];
   const int C = a.C0 + a.C1;
-  const int cv = C / VEC;
   const int b = blockIdx.y;
-  float* s_sc = s_par;
-  float* s_sh = s_par + C;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_sc[i] = a.scale[(long long)b * C + i];
-    s_sh[i] = a.shift[(long long)b * C + i];
+  const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
+  const int c = cvi * VEC;
+  float sc[VEC], sh[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    sc[j] = a.scale[(long long)b * C + c + j];
+    sh[j] = a.shift[(long long)b * C + c + j];
   }
-  __syncthreads();
-  // per-sample index space fits 32 bits (voxels * C/VEC <= 2^31): keep the div/mod 32-bit
-  const unsigned total = (unsigned)(a.voxels * cv);
-  const unsigned stride = gridDim.x * blockDim.x;
-  const long long vbase = (long long)b * a.voxels;
-  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNROLL) {
+  const int es = TF32 ? 4 : 2;
+  const bool first = c < a.C0;
+  const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 + c) * es
+                          : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 + (c - a.C0)) * es;
+  const long long src_stride = (first ? a.ld0 : a.ld1) * es;  // bytes per voxel
+  char* dst = (char*)a.y + ((long long)b * a.voxels * C + c) * es;
+  const long long dst_stride = (long long)C * es;
+  const long long step = (long long)gridDim.x * k;
+  for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
     uint4 raw[UNROLL];
-    int cc[UNROLL];
-    long long vv[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const unsigned i = i0 + u * stride;
-      if (i < total) {
-        const unsigned vox = i / (unsigned)cv;
-        const int c = (int)(i - vox * (unsigned)cv) * VEC;
-        const long long bv = vbase + vox;
-        cc[u] = c; vv[u] = bv;
-        const char* src;
-        if (TF32) src = (const char*)((c < a.C0) ? (const float*)a.x0 + bv * a.ld0 + c : (const float*)a.x1 + bv * a.ld1 + (c - a.C0));
-        else src = (const char*)((c < a.C0) ? (const __nv_bfloat16*)a.x0 + bv * a.ld0 + c : (const __nv_bfloat16*)a.x1 + bv * a.ld1 + (c - a.C0));
-        raw[u] = __ldg((const uint4*)src);
-      }
+      const long long v = v0 + u * step;
+      if (v < a.voxels) raw[u] = __ldg((const uint4*)(src + v * src_stride));
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const unsigned i = i0 + u * stride;
-      if (i >= total) continue;
-      const int c = cc[u];
-      float v[VEC];
+      const long long v = v0 + u * step;
+      if (v >= a.voxels) continue;
+      float x[VEC];
       if (TF32) {
         const float* f = (const float*)&raw[u];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) v[j] = f[j];
+        for (int j = 0; j < VEC; ++j) x[j] = f[j];
       } else {
         const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[u];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        float y = v[j] * s_sc[c + j] + s_sh[c + j];
+        float y = fmaf(x[j], sc[j], sh[j]);
         if (a.silu) y = TF32 ? silu_f(y) : silu_fast(y);
-        v[j] = y;
+        x[j] = y;
       }
       if (TF32) {
-        float4 t = make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
-        *((float4*)((float*)a.y + vv[u] * C + c)) = t;
+        *((float4*)(dst + v * dst_stride)) =
+            make_float4(round_tf32_rna(x[0]), round_tf32_rna(x[1]), round_tf32_rna(x[2]), round_tf32_rna(x[3]));
       } else {
         uint4 t;
         __nv_bfloat162* h = (__nv_bfloat162*)&t;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        *((uint4*)((__nv_bfloat16*)a.y + vv[u] * C + c)) = t;
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+        *((uint4*)(dst + v * dst_stride)) = t;
       }
     }
   }
@@ -145,15 +138,17 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a) {
 void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s) {
   const int vec = a.tf32 ? 4 : 8;
   const int C = a.C0 + a.C1;
-  const long long per_sample = a.voxels * (C / vec);
-  long long gx = (per_sample + 256 * 4 - 1) / (256 * 4);
+  const int cv = C / vec;
+  if (cv > 256 || cv < 1 || a.C0 % vec != 0) throw std::runtime_error("mdb: unsupported channel count in norm_act");
+  const int k = 256 / cv;  // voxels per block pass
+  const int threads = cv * k;
+  long long gx = (a.voxels + (long long)k * 4 - 1) / ((long long)k * 4);
   const long long cap = (148LL * 8 + B - 1) / B;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)B);
-  const size_t smem = 2 * C * sizeof(float);
-  if (a.tf32) norm_act_kernel<true><<<grid, 256, smem, s>>>(a);
-  else norm_act_kernel<false><<<grid, 256, smem, s>>>(a);
+  if (a.tf32) norm_act_kernel<true><<<grid, threads, 0, s>>>(a, cv, k);
+  else norm_act_kernel<false><<<grid, threads, 0, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
 }
 

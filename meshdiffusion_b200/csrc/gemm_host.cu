@@ -91,8 +91,11 @@ void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N,
   p.osx = osx; p.osy = osy; p.osz = osz; p.osb = osb;
   p.out_fp32 = out_fp32 ? 1 : 0;
   {
+    // TF32 operands: tensor cores truncate fp32 inputs to 10 mantissa bits; rounding the stored activations to
+    // nearest instead removes that systematic bias (measured on the full res64 net: rel-L2 vs fp32 2.5e-3 -> 1.5e-3,
+    // on par with stock cuDNN/cuBLAS TF32). MDB_TF32_ROUND_STORE=0 restores plain fp32 stores.
     const char* e = getenv("MDB_TF32_ROUND_STORE");
-    p.round_out = (prec == kTF32 && !out_fp32 && e && e[0] == '1') ? 1 : 0;
+    p.round_out = (prec == kTF32 && !out_fp32 && !(e && e[0] == '0')) ? 1 : 0;
   }
   p.alpha = 1.f;
   p.ocs = 1;
