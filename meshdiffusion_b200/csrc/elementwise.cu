@@ -371,6 +371,50 @@ void launch_dense(const float* x, const float* w, const float* bias, float* out,
   MDB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------ head conv phase 2: tap shift-sum (Cout == 4)
+template <bool PFP32>
+__global__ void __launch_bounds__(256) tap_shift_sum_kernel(const void* __restrict__ P, long long ldp, const float* __restrict__ bias,
+                                                           float* __restrict__ out, int R, int k) {
+  const int pad = k / 2;
+  const long long V = (long long)R * R * R;
+  const int b = blockIdx.y;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(v % R), y = (int)((v / R) % R), z = (int)(v / ((long long)R * R));
+    float acc0 = bias[0], acc1 = bias[1], acc2 = bias[2], acc3 = bias[3];
+    int tap = 0;
+    for (int dz = -pad; dz <= pad; ++dz)
+      for (int dy = -pad; dy <= pad; ++dy)
+        for (int dx = -pad; dx <= pad; ++dx, ++tap) {
+          const int zz = z + dz, yy = y + dy, xx = x + dx;
+          if ((unsigned)zz >= (unsigned)R || (unsigned)yy >= (unsigned)R || (unsigned)xx >= (unsigned)R) continue;
+          const long long row = ((long long)b * V + ((long long)zz * R + yy) * R + xx) * ldp + tap * 4;
+          if (PFP32) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P) + row));
+            acc0 += t.x; acc1 += t.y; acc2 += t.z; acc3 += t.w;
+          } else {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(P) + row));
+            const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+            acc0 += f0.x; acc1 += f0.y; acc2 += f1.x; acc3 += f1.y;
+          }
+        }
+    float* o = out + (long long)b * 4 * V + v;
+    o[0] = acc0; o[V] = acc1; o[2 * V] = acc2; o[3 * V] = acc3;
+  }
+}
+void launch_tap_shift_sum(const void* P, long long ldp, int p_fp32, const float* bias, float* out, int B, int R, int k,
+                          int Cout, cudaStream_t s) {
+  if (Cout != 4) throw std::runtime_error("mdb: tap_shift_sum supports 4 output channels");
+  const long long V = (long long)R * R * R;
+  long long gx = (V + 255) / 256;
+  const long long cap = (148LL * 16 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)B);
+  if (p_fp32) tap_shift_sum_kernel<true><<<grid, 256, 0, s>>>(P, ldp, bias, out, R, k);
+  else tap_shift_sum_kernel<false><<<grid, 256, 0, s>>>(P, ldp, bias, out, R, k);
+  MDB_LAUNCH_CHECK();
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] + (b ? b[i] : 0.f);
 }

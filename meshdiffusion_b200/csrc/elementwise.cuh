@@ -46,6 +46,11 @@ void launch_temb(const float* labels, const float* w0, const float* b0, const fl
 // out[b][n] = W[n][:] . x[b][:] + bias[n]   (all Dense_0 projections at once)
 void launch_dense(const float* x, const float* w, const float* bias, float* out, int B, int K, int N, cudaStream_t s);
 
+// Head convolution, second phase: out[b][co][v] = bias[co] + sum_taps P[b][v + off(tap)][tap*Cout + co] (zero outside the
+// grid). P holds the per-tap projections of the normalised activations ([B][V][ldp], activation dtype or fp32).
+void launch_tap_shift_sum(const void* P, long long ldp, int p_fp32, const float* bias, float* out, int B, int R, int k,
+                          int Cout, cudaStream_t s);
+
 void launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
 
 // Ancestral-sampling predictor update fused with the score scaling and both mask multiplies

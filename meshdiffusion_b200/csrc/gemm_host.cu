@@ -214,6 +214,7 @@ void GemmOp::add_pointwise_w(const std::vector<Act>& srcs, const WSrc* w) {
 
 void GemmOp::set_residual(const void* res, long long ldr, long long batch_stride, bool fp32) {
   p.res = res;
+  p.batch_fastest = batch_stride == 0 ? 1 : 0;  // a residual shared by every sample: keep its slice L2-resident
   p.rsx = ldr; p.rsy = ldr * p.X; p.rsz = ldr * p.X * p.Y; p.rsb = batch_stride;
   p.res_fp32 = fp32 ? 1 : 0;
 }
@@ -233,7 +234,7 @@ void GemmOp::set_b_activation(void* ptr, int K, int N, int batch, long long rs, 
 }
 
 // ------------------------------------------------------------------ weight packing (device gather)
-struct PackWSrc { const float* ptr; long long sn, sc, st; int cvalid; };
+struct PackWSrc { const float* ptr; long long sn, sc, st; int cvalid; int ndiv; long long sn_hi; };
 struct PackArgs { PackWSrc w[4]; };
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -260,7 +261,10 @@ __global__ void pack_weights_kernel(const LoadEntry* __restrict__ loads, const i
     const int c = e.wc0 + cc;
     const PackWSrc w = args.w[e.wsrc];
     float v = 0.f;
-    if (c < w.cvalid) v = w.ptr[n * w.sn + c * w.sc + tap * w.st];
+    if (c < w.cvalid) {
+      const long long noff = w.ndiv ? (long long)(n % w.ndiv) * w.sn + (long long)(n / w.ndiv) * w.sn_hi : (long long)n * w.sn;
+      v = w.ptr[noff + c * w.sc + tap * w.st];
+    }
     if (TF32) reinterpret_cast<float*>(out)[idx] = round_tf32(v);
     else reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16(v);
   }
@@ -280,7 +284,7 @@ void GemmOp::repack(cudaStream_t stream) {
   MDB_CUDA_CHECK(cudaMemcpyAsync(d_b, ks0.data(), ks0.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   if (wsrcs.size() > 4) throw std::runtime_error("mdb: too many weight sources");
   PackArgs args{};
-  for (size_t i = 0; i < wsrcs.size(); ++i) args.w[i] = {wsrcs[i].ptr, wsrcs[i].sn, wsrcs[i].sc, wsrcs[i].st, wsrcs[i].cvalid};
+  for (size_t i = 0; i < wsrcs.size(); ++i) args.w[i] = {wsrcs[i].ptr, wsrcs[i].sn, wsrcs[i].sc, wsrcs[i].st, wsrcs[i].cvalid, wsrcs[i].ndiv, wsrcs[i].sn_hi};
   const long long total = 1LL * ksteps * kb_elems(prec) * p.N;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

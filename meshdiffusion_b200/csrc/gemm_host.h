@@ -37,6 +37,9 @@ struct WSrc {
   const float* ptr = nullptr;
   long long sn = 0, sc = 0, st = 0;
   int cvalid = 0;
+  // optional split of the output index: n -> (n / ndiv, n % ndiv) addressed with strides (sn_hi, sn)
+  int ndiv = 0;
+  long long sn_hi = 0;
 };
 
 struct Geometry { int bx, by, bz, bb; };

@@ -70,6 +70,7 @@ struct GemmParams {
   int n_tiles_n;
   int N;               // valid output columns
   int b_batched;       // B tensor map has a batch coordinate following the tile's sample
+  int batch_fastest;   // enumerate the batch axis first among M-tiles (residual shared by all samples stays in L2)
   int kb_elems;        // K elements per k-step (64 bf16 / 32 tf32)
   // epilogue
   void* out;
@@ -165,10 +166,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0) {
     int nt = tile % p.n_tiles_n;
     int mt = tile / p.n_tiles_n;
+    int bt = 0;
+    if (p.batch_fastest) { bt = mt % p.tb; mt /= p.tb; }
     int xt = mt % p.tx; mt /= p.tx;
     int yt = mt % p.ty; mt /= p.ty;
     int zt = mt % p.tz; mt /= p.tz;
-    x0 = xt * p.bx; y0 = yt * p.by; z0 = zt * p.bz; b0 = mt * p.bb; n0 = nt * BLOCK_N;
+    if (!p.batch_fastest) bt = mt;
+    x0 = xt * p.bx; y0 = yt * p.by; z0 = zt * p.bz; b0 = bt * p.bb; n0 = nt * BLOCK_N;
   };
 
   if (warp == 0) {
@@ -286,6 +290,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         s_bias[i] = bv;
       }
       named_bar_sync(1, 128);  // also orders the previous tile's statistics reads before this tile's writes
+      // residual rows do not depend on the accumulator: fetch the first chunk while waiting for the MMAs, and every
+      // next chunk while the current one is being stored, so the (L2/HBM) latency is never exposed
+      uint4 rbuf[8];
+      auto prefetch_res = [&](int ch) {
+        const int nbp = n0 + ch * 32;
+        if (!(p.res && valid && p.ocs == 1 && nbp + 32 <= p.N)) return;
+        if (TF32 || p.res_fp32) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + roff + nbp);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rbuf[i] = __ldg(rp + i);
+        } else {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nbp);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rbuf[i] = __ldg(rp + i);
+        }
+      };
+      prefetch_res(0);
       mbar_wait(t_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
@@ -311,23 +332,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) * p.alpha + mbias + sb[i];
         if (p.res && valid) {
           if (TF32 || p.res_fp32) {
-            const float* rp = reinterpret_cast<const float*>(p.res) + roff + nb;
             if (full) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float4 t = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                const float4 t = *reinterpret_cast<const float4*>(&rbuf[i]);
                 v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
               }
             } else {
+              const float* rp = reinterpret_cast<const float*>(p.res) + roff + nb;
               for (int i = 0; i < 32; ++i) if (nb + i < p.N) v[i] += rp[i];
             }
           } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nb;
             if (full) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                uint4 t = __ldg(reinterpret_cast<const uint4*>(rp) + i);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rbuf[i]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   float2 f = __bfloat1622float2(h[j]);
@@ -335,10 +354,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 }
               }
             } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nb;
               for (int i = 0; i < 32; ++i) if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
             }
           }
         }
+        if (ch + 1 < BLOCK_N / 32) prefetch_res(ch + 1);  // lands while this chunk is stored / reduced
         if (valid) {
           if (TF32 || p.out_fp32) {
             float* op = reinterpret_cast<float*>(p.out) + ooff + nb;

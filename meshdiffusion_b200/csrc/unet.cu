@@ -458,7 +458,29 @@ void UNet::build() {
   float* hw = P("all_modules." + std::to_string(m) + ".weight", {Cin, nf, k, k, k});
   float* hb = P("all_modules." + std::to_string(m) + ".bias", {Cin});
   ++m;
-  if (!dry_) {
+  // The head has only `Cin` (= 4) output channels: as an implicit GEMM it would stream all 27/125 shifted A tiles for
+  // an N=4 product. Instead: (1) ONE unshifted GEMM projects every voxel onto all taps at once,
+  //   P[v][tap*Cout + co] = sum_c a[v][c] * W[co][c][tap]      (N = taps*Cout = 108 / 500, K = nf),
+  // (2) a bandwidth kernel gathers out[v][co] = bias[co] + sum_tap P[v + off(tap)][tap*Cout + co].
+  if (Cin == 4) {
+    const int Np = ((T * Cin + 7) / 8) * 8;
+    const bool pf32 = prec_ == kTF32;
+    auto Pt = std::make_shared<Tens>();
+    Pt->bytes = (size_t)mb * V0 * Np * (pf32 ? 4 : 2);
+    Pt->off = arena_.alloc(Pt->bytes);
+    Pt->ptr = dry_ ? nullptr : arena_base_ + Pt->off;
+    if (!dry_) {
+      GemmOp* g = new_gemm("head.proj");
+      g->set_output(prec_, R0, R0, R0, mb, T * Cin, Pt->ptr, Np, pf32);
+      WSrc ws{hw, (long long)nf * T, (long long)T, 0, nf, Cin, 1};
+      g->add_pointwise_w({act_of(a)}, &ws);
+      g->finalize(0, false);
+      add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
+      const void* pp = Pt->ptr;
+      add_step("head.shift_sum", [=](cudaStream_t s, int B) { launch_tap_shift_sum(pp, Np, pf32 ? 1 : 0, hb, rt_out_, B, R0, k, Cin, s); });
+    }
+    arena_.release(Pt->off);
+  } else if (!dry_) {
     GemmOp* g = new_gemm("head.conv");
     g->set_output_strided(prec_, R0, R0, R0, mb, Cin, nullptr, 1, R0, (long long)R0 * R0, (long long)Cin * V0, true);
     g->set_out_col_stride(V0);
