@@ -27,7 +27,8 @@ constexpr int kAStageRows = 160;                     // 128 + up to 32 halo rows
 constexpr int kAStageBytes = kAStageRows * kRowBytes;  // 20480, multiple of 1024
 constexpr int kMaxLoads = 2048;
 constexpr int kMaxAMaps = 10;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 
 struct __align__(16) LoadEntry {
   uint8_t tmap;   // index of the A tensor map
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, kEpiThreads / 32); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -257,9 +258,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // 8 epilogue warps: warp w reads TMEM lanes 32*(w%4).. (hardware rule) and owns the column chunks
+    // {half, half+2, ...}; two warps per lane quarter double the latency hiding of the drain.
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunks = BLOCK_N / 32;
+    constexpr int kChunkStep = kChunks >= 2 ? 2 : 1;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..127
+    const int et = threadIdx.x - 128;  // 0..255
     const int rows_per_b = p.bx * p.by * p.bz;
     const int seg = row / rows_per_b;  // which sample of the tile this row belongs to (warp-uniform by construction)
     int it = 0;
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
       // stage bias + per-sample (time-embedding) bias of this tile's columns: s_bias[seg][col]
       float* s_bias = s_stats + 8 * BLOCK_N + (it & 1) * 4 * BLOCK_N;  // double-buffered across tiles
-      for (int i = et; i < p.bb * BLOCK_N; i += 128) {
+      for (int i = et; i < p.bb * BLOCK_N; i += kEpiThreads) {
         const int sg = i / BLOCK_N, c = i % BLOCK_N;
         const int n = n0 + c, bgl = b0 + sg;
         float bv = 0.f;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         s_bias[i] = bv;
       }
-      named_bar_sync(1, 128);  // also orders the previous tile's statistics reads before this tile's writes
+      named_bar_sync(1, kEpiThreads);  // also orders the previous tile's statistics reads before this tile's writes
       // residual rows do not depend on the accumulator: fetch the first chunk while waiting for the MMAs, and every
       // next chunk while the current one is being stored, so the (L2/HBM) latency is never exposed
       uint4 rbuf[8];
@@ -306,17 +312,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           for (int i = 0; i < 4; ++i) rbuf[i] = __ldg(rp + i);
         }
       };
-      prefetch_res(0);
+      const int ch0 = kChunkStep == 2 ? half : 0;
+      const bool active = kChunkStep == 2 || half == 0;  // BLOCK_N == 32: one chunk, the second warp of a quarter idles
+      if (active) prefetch_res(ch0);
       mbar_wait(t_full + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      if (!active) {  // nothing to drain for this warp: still release its share of the TMEM stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+      }
+      for (int ch = ch0; ch < kChunks && active; ch += kChunkStep) {
         uint32_t rr[32];
         tmem_ld32(t_row + ch * 32, rr);
         tmem_ld_wait();
-        if (ch == BLOCK_N / 32 - 1) {
+        if (ch + kChunkStep >= kChunks) {
           // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
           }
         }
-        if (ch + 1 < BLOCK_N / 32) prefetch_res(ch + 1);  // lands while this chunk is stored / reduced
+        if (ch + kChunkStep < kChunks) prefetch_res(ch + kChunkStep);  // lands while this chunk is stored / reduced
         if (valid) {
           if (TF32 || p.out_fp32) {
             float* op = reinterpret_cast<float*>(p.out) + ooff + nb;
@@ -417,9 +430,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
       }
       if (p.stats) {
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         const int warps_per_seg = rows_per_b >= 128 ? 4 : rows_per_b / 32;
-        for (int i = et; i < p.bb * BLOCK_N; i += 128) {
+        for (int i = et; i < p.bb * BLOCK_N; i += kEpiThreads) {
           const int sg = i / BLOCK_N, c = i % BLOCK_N;
           const int bgl = b0 + sg, n = n0 + c;
           if (bgl < p.Bn && n < p.N) {
