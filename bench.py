@@ -33,6 +33,12 @@ UNIT = "sample-steps/s"
 N_EVALS_FULL = 999  # pc_sampler's unconditional loop evaluates the network N-1 = 999 times (sampling.py:471)
 
 
+def host_threads():
+    """oneDNN conv3d scales to ~32 threads on this host class and gets slower beyond (measured on the 128-core GPU box:
+    16 thr 6.7 s, 32 thr 6.1 s, 64 thr 8.3 s, 128 thr 46 s per res64 forward) -- use what is actually useful."""
+    return int(os.environ.get("MDB_CPU_THREADS", min(32, os.cpu_count() or 1)))
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -237,7 +243,7 @@ def _is_conv_gemm(name):
 def cpu_baseline_port(net, mask, steps=1, threads=None):
     """Oracle port of the reference network + update on the host cores: B=1, `steps` steps after one warm-up."""
     from oracle import sampler_oracle, unet_oracle
-    threads = threads or os.cpu_count()
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     arch = dict(net.arch)
@@ -274,7 +280,7 @@ def run_reference(args):
     torch.manual_seed(0)
     net = mutils.create_model(cfg, use_parallel=False)
     random_init_nondegenerate(net)
-    threads = os.cpu_count()
+    threads = host_threads()
     torch.set_num_threads(threads)
     R = 64
     mask = grid_mask_from_tets(R).view(1, R, R, R)
