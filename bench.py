@@ -109,6 +109,7 @@ def run_ours(args):
     device = torch.device(f"cuda:{local}")
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     B, R, K, W = args.batch, 64, args.steps, args.warmup

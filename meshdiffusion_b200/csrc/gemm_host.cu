@@ -45,6 +45,15 @@ static void encode_map(CUtensorMap* m, Precision prec, int rank, void* base, con
   }
 }
 
+static int sm_count_or_default() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 148;
+  }
+  return n;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -87,6 +96,12 @@ void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N,
   p.N = N;
   block_n = N <= 32 ? 32 : 128;
   p.n_tiles_n = (N + block_n - 1) / block_n;
+  {
+    // CTA pairs (tcgen05 cta_group::2) whenever there are enough M-tiles to keep all 74 pairs busy
+    const char* e = getenv("MDB_CTA_PAIRS");
+    const int tiles_m = p.tx * p.ty * p.tz * p.tb;
+    pair = block_n == 128 && tiles_m * p.n_tiles_n >= 2 * (sm_count_or_default() / 2) && !(e && e[0] == '0');
+  }
   p.out = out;
   p.osx = osx; p.osy = osy; p.osz = osz; p.osb = osb;
   p.out_fp32 = out_fp32 ? 1 : 0;
@@ -222,7 +237,7 @@ void GemmOp::set_residual(const void* res, long long ldr, long long batch_stride
 void GemmOp::encode_bmap(void* ptr, int K, int N, int batch, long long rsb, long long bsb) {
   uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)batch};
   uint64_t strides[2] = {(uint64_t)rsb, (uint64_t)bsb};
-  uint32_t box[3] = {(uint32_t)kb_elems(prec), (uint32_t)block_n, 1};
+  uint32_t box[3] = {(uint32_t)kb_elems(prec), (uint32_t)(pair ? block_n / 2 : block_n), 1};
   encode_map(&p.bmap, prec, 3, ptr, dims, strides, box);
 }
 
@@ -306,8 +321,8 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   p.n_loads = (int)loads.size();
   // pipeline segments: runs of identical entries; plain (nk == 1) entries are paired two per stage
   {
-    const int btile = block_n * kRowBytes;
-    const int stage_bytes = kAStageBytes + 3 * 128 * kRowBytes;
+    const int btile = block_n * kRowBytes / (pair ? 2 : 1);
+    const int stage_bytes = pair ? (2 * 128 * kRowBytes + 2 * 64 * kRowBytes) : (kAStageBytes + 3 * 128 * kRowBytes);
     p.n_segs = 0;
     auto push = [&](int n_groups, int epg, const LoadEntry& e) {
       if (n_groups <= 0) return;
@@ -346,15 +361,29 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
-template <int BN, bool TF32>
+template <int BN, bool TF32, bool CG2>
 static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, TF32>;
+  auto kern = gemm_tc_kernel<BN, TF32, CG2>;
+  constexpr int smem = GemmCfg<BN, CG2>::kSmemBytes;
   if (!configured) {
-    MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(p);
+  if (CG2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<grid, kGemmThreads, smem, stream>>>(p);
+  }
   MDB_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -366,11 +395,19 @@ void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
     p.tb = (B + p.bb - 1) / p.bb;
   }
   if (out_override) p.out = out_override;
-  const int total = p.tx * p.ty * p.tz * p.tb * p.n_tiles_n;
-  int grid = total < sm_count() ? total : sm_count();
+  const int tiles_m = p.tx * p.ty * p.tz * p.tb;
   const bool tf = prec == kTF32;
-  if (block_n == 32) { if (tf) launch_impl<32, true>(p, grid, stream); else launch_impl<32, false>(p, grid, stream); }
-  else { if (tf) launch_impl<128, true>(p, grid, stream); else launch_impl<128, false>(p, grid, stream); }
+  if (pair) {
+    const int work = ((tiles_m + 1) / 2) * p.n_tiles_n;
+    const int pairs = sm_count() / 2;
+    const int grid = 2 * (work < pairs ? work : pairs);
+    if (tf) launch_impl<128, true, true>(p, grid, stream); else launch_impl<128, false, true>(p, grid, stream);
+    return;
+  }
+  const int total = tiles_m * p.n_tiles_n;
+  int grid = total < sm_count() ? total : sm_count();
+  if (block_n == 32) { if (tf) launch_impl<32, true, false>(p, grid, stream); else launch_impl<32, false, false>(p, grid, stream); }
+  else { if (tf) launch_impl<128, true, false>(p, grid, stream); else launch_impl<128, false, false>(p, grid, stream); }
 }
 
 }  // namespace mdb

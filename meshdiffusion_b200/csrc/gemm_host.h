@@ -50,6 +50,7 @@ class GemmOp {
   GemmParams p{};
   Precision prec = kBF16;
   int block_n = 128;
+  bool pair = false;  // CTA-pair kernel (cta_group::2)
   std::vector<LoadEntry> loads;
   std::vector<WSrc> wsrcs;
   int n_amaps = 0;

@@ -90,12 +90,13 @@ struct GemmParams {
   long long* stats;  // [Bn][N][2] (sum, sumsq) in 2^-24 fixed point (order-independent accumulation) or null
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CG2>
 struct GemmCfg {
-  static constexpr int kStages = 3;
-  static constexpr int kBTileBytes = BLOCK_N * kRowBytes;
-  // a stage holds one halo box + 3 weight tiles of 128 rows (68 KB), or 2 plain boxes + 2 tiles (64 KB)
-  static constexpr int kStageBytes = kAStageBytes + 3 * 128 * kRowBytes;
+  static constexpr int kStages = CG2 ? 4 : 3;
+  // weight tile bytes staged per CTA per k-step (a CTA pair splits the N rows of the tile between its two CTAs)
+  static constexpr int kBTileBytes = BLOCK_N * kRowBytes / (CG2 ? 2 : 1);
+  // a stage holds one halo box + 3 weight tiles, or 2 plain boxes + 2 tiles
+  static constexpr int kStageBytes = CG2 ? (2 * 128 * kRowBytes + 2 * 64 * kRowBytes) : (kAStageBytes + 3 * 128 * kRowBytes);
   // The whole TMEM (512 columns) is taken: with one CTA per SM the allocation then always starts at column 0, so
   // accumulator addresses are compile-time/uniform values and the MMA issue loop needs no per-instruction R2UR.
   static constexpr int kTmemCols = 512;
@@ -125,9 +126,71 @@ __device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t
   }
 }
 
-template <int BLOCK_N, bool TF32>
+// ---------------------------------------------------------------- CTA-pair (cta_group::2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_5d_cg2(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_lo_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+  }
+}
+// commit of a cta_group::2 MMA batch: arrives on the mbarrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(512) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(512) : "memory");
+}
+
+// CG2 = CTA pair: the two CTAs of a 2-cluster own adjacent M-tiles; the leader's single thread issues
+// tcgen05.mma.cta_group::2 (M = 256) over both, each CTA stages its own A box and HALF of every weight tile, so the
+// per-SM L2->SMEM traffic, the shared-memory operand reads and the MMA issue count per FLOP all drop.
+template <int BLOCK_N, bool TF32, bool CG2>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CG2>;
   constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -145,15 +208,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&p.amap[i]);
     tma_prefetch_desc(&p.bmap);
   }
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, kEpiThreads / 32); }
+    // the leader's t_empty collects the epilogue warps of BOTH CTAs of a pair
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, (CG2 ? 2 : 1) * kEpiThreads / 32); }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(s_tmem));
+  if (warp == 2) {
+    if constexpr (CG2) tmem_alloc_pair(smem_u32(s_tmem));
+    else tmem_alloc<Cfg::kTmemCols>(smem_u32(s_tmem));
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = 0;
   if (*s_tmem != 0) {
@@ -162,24 +230,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   }
 
   const int tiles_m = p.tx * p.ty * p.tz * p.tb;
-  const int total_tiles = tiles_m * p.n_tiles_n;
+  // work items: (M-tile, N-tile) for a single CTA, (pair of adjacent M-tiles, N-tile) for a CTA pair
+  const int total_tiles = (CG2 ? (tiles_m + 1) / 2 : tiles_m) * p.n_tiles_n;
+  const int first_tile = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0) {
     int nt = tile % p.n_tiles_n;
     int mt = tile / p.n_tiles_n;
+    if (CG2) mt = 2 * mt + (int)rank;
+    n0 = nt * BLOCK_N;
+    if (mt >= tiles_m) {  // odd tile count: the pair's second CTA gets an empty tile (all loads zero-filled, no stores)
+      x0 = 0; y0 = 0; z0 = 0; b0 = p.tb * p.bb;
+      return;
+    }
     int bt = 0;
     if (p.batch_fastest) { bt = mt % p.tb; mt /= p.tb; }
     int xt = mt % p.tx; mt /= p.tx;
     int yt = mt % p.ty; mt /= p.ty;
     int zt = mt % p.tz; mt /= p.tz;
     if (!p.batch_fastest) bt = mt;
-    x0 = xt * p.bx; y0 = yt * p.by; z0 = zt * p.bz; b0 = bt * p.bb; n0 = nt * BLOCK_N;
+    x0 = xt * p.bx; y0 = yt * p.by; z0 = zt * p.bz; b0 = bt * p.bb;
   };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t st = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       int x0, y0, z0, b0, n0;
       decode(tile, x0, y0, z0, b0, n0);
       int kcol = 0, l = 0;
@@ -196,16 +273,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(empty + 8 * st, ph ^ 1);
           if (elect_one()) {
             const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
-            const uint32_t bar = full + 8 * st;
-            mbar_expect_tx(bar, group_bytes);
             int kc = kcol;
-            for (int e = 0; e < seg.epg; ++e) {
-              const uint4 raw = e == 0 ? raw0 : raw1;
-              const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
-              tma_load_5d(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
-              for (int j = 0; j < seg.nk; ++j) {
-                tma_load_3d(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, n0, bcoord);
-                kc += p.kb_elems;
+            if constexpr (CG2) {
+              // both CTAs credit the LEADER's full barrier; only the leader arms it (with the pair's total bytes)
+              const uint32_t bar = mapa_u32(full + 8 * st, 0);
+              if (rank == 0) mbar_expect_tx(full + 8 * st, 2 * group_bytes);
+              const int nh = n0 + (int)rank * (BLOCK_N / 2);
+              for (int e = 0; e < seg.epg; ++e) {
+                const uint4 raw = e == 0 ? raw0 : raw1;
+                const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
+                tma_load_5d_cg2(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
+                for (int j = 0; j < seg.nk; ++j) {
+                  tma_load_3d_cg2(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, nh, bcoord);
+                  kc += p.kb_elems;
+                }
+              }
+            } else {
+              const uint32_t bar = full + 8 * st;
+              mbar_expect_tx(bar, group_bytes);
+              for (int e = 0; e < seg.epg; ++e) {
+                const uint4 raw = e == 0 ? raw0 : raw1;
+                const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
+                tma_load_5d(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
+                for (int j = 0; j < seg.nk; ++j) {
+                  tma_load_3d(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, n0, bcoord);
+                  kc += p.kb_elems;
+                }
               }
             }
           }
@@ -216,12 +309,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc(TF32, kBlockM, BLOCK_N);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    constexpr uint32_t idesc = make_idesc(TF32, CG2 ? 2 * kBlockM : kBlockM, BLOCK_N);
     uint32_t st = 0, ph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(t_empty + 8 * acc, acc_phase ^ 1);
@@ -242,18 +335,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                 const uint32_t b_lo = desc_lo(sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes);
 #pragma unroll
                 for (int k = 0; k < kRowBytes / 32; ++k) {
-                  umma_lo<TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accumulate);
+                  if constexpr (CG2) umma_lo_cg2<TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accumulate);
+                  else umma_lo<TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accumulate);
                   accumulate = 1;
                 }
               }
             }
-            umma_commit(empty + 8 * st);
+            if constexpr (CG2) umma_commit_pair(empty + 8 * st); else umma_commit(empty + 8 * st);
           }
           __syncwarp();
           if (++st == NS) { st = 0; ph ^= 1; }
         }
       }
-      if (elect_one()) umma_commit(t_full + 8 * acc);
+      if (elect_one()) { if constexpr (CG2) umma_commit_pair(t_full + 8 * acc); else umma_commit(t_full + 8 * acc); }
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -269,7 +363,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int rows_per_b = p.bx * p.by * p.bz;
     const int seg = row / rows_per_b;  // which sample of the tile this row belongs to (warp-uniform by construction)
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int x0, y0, z0, b0, n0;
@@ -323,7 +417,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (!active) {  // nothing to drain for this warp: still release its share of the TMEM stage
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+        if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive(t_empty + 8 * acc); }
       }
       for (int ch = ch0; ch < kChunks && active; ch += kChunkStep) {
         uint32_t rr[32];
@@ -333,7 +427,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+          if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive(t_empty + 8 * acc); }
         }
         const int nb = n0 + ch * 32;
         if (nb >= p.N) continue;  // warp-uniform
@@ -451,10 +545,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all(); else __syncthreads();  // pair: nobody leaves while its peer may still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (CG2) tmem_dealloc_pair(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
