@@ -83,6 +83,24 @@ int mdb_sampler_run(mdb_unet* net, float* x, float* x_mean, const float* mask, c
                     float* eps_buf, float* labels_buf, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Training-step kernels (optimiser side). Replace get_ddpm_loss_fn's elementwise tail (lib/diffusion/losses.py:69-78),
+ * torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (losses.py:45-50, 26-35) and
+ * ExponentialMovingAverage.update (lib/diffusion/models/ema.py:43-64). Pointer tables / numels are DEVICE arrays of
+ * n entries (one per parameter tensor); `scratch` is one device double. The network backward is not part of round 1.
+ */
+/* loss = mean_b[mean_{c,v}((pred-noise)^2 mask[v])] * V / mask_sum -> *loss_out; grad_pred (nullable) = dloss/dpred. */
+int mdb_ddpm_loss(const float* pred, const float* noise, const float* mask, double mask_sum, float* loss_out,
+                  float* grad_pred, double* scratch, int batch, int channels, long long voxels, void* stream);
+/* coef = min(1, max_norm / (||g||_2 + 1e-6)) over all tensors -> *coef_out (and the norm in *total_norm_out). */
+int mdb_grad_clip_coef(const float* const* grads_dev, const long long* numels_dev, int n, float max_norm,
+                       float* coef_out, float* total_norm_out, double* scratch, void* stream);
+/* g *= *clip_coef (nullable); Adam(lr, beta1, beta2, eps, step >= 1, no weight decay); ema -= (1-decay)(ema - p). */
+int mdb_adam_ema_step(float* const* params_dev, const float* const* grads_dev, float* const* exp_avg_dev,
+                      float* const* exp_avg_sq_dev, float* const* ema_dev, const long long* numels_dev, int n, float lr,
+                      float beta1, float beta2, float eps, int step, const float* clip_coef_dev, float ema_decay,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Operator-level entry points (parity tests call these like the reference's renderutils tests call its ops).
  * Activations are NDHWC in the operand dtype of `precision` (bf16 or fp32).
  */

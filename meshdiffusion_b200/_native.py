@@ -52,6 +52,9 @@ SIGNATURES = {
     "mdb_fingerprint": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mdb_sampler_update": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _u64, _u64, _vp]),
     "mdb_sampler_run": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_f), _i, _i, _u64, _vp, _vp, _vp]),
+    "mdb_ddpm_loss": (_i, [_vp, _vp, _vp, _d, _vp, _vp, _vp, _i, _i, _ll, _vp]),
+    "mdb_grad_clip_coef": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "mdb_adam_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "mdb_conv3d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "mdb_groupnorm_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp]),
     "mdb_marching_tets_prepare": (_i, [_vp, _i, _i, _i, ctypes.POINTER(_vp)]),
