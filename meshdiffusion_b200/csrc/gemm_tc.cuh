@@ -100,7 +100,7 @@ struct GemmCfg {
   // The whole TMEM (512 columns) is taken: with one CTA per SM the allocation then always starts at column 0, so
   // accumulator addresses are compile-time/uniform values and the MMA issue loop needs no per-instruction R2UR.
   static constexpr int kTmemCols = 512;
-  static constexpr int kStatsFloats = 16 * BLOCK_N;  // [4 warps][sum,sumsq][N] column partials + 2 x [4 segs][N] bias
+  static constexpr int kStatsFloats = 24 * BLOCK_N;  // 2 x [4 warps][sum,sumsq][N] column partials + 2 x [4 segs][N] bias
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatsFloats * 4 +
                                     (2 * kStages + 4) * 8 + 16;
 };
@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int rows_per_b = p.bx * p.by * p.bz;
     const int seg = row / rows_per_b;  // which sample of the tile this row belongs to (warp-uniform by construction)
     int it = 0;
+    int staged_n0 = -1, staged_b0 = -1, bias_buf = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -377,19 +378,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const long long ooff = xg * p.osx + yg * p.osy + zg * p.osz + bg * p.osb;
       const long long roff = xg * p.rsx + yg * p.rsy + zg * p.rsz + bg * p.rsb;
 
-      // stage bias + per-sample (time-embedding) bias of this tile's columns: s_bias[seg][col]
-      float* s_bias = s_stats + 8 * BLOCK_N + (it & 1) * 4 * BLOCK_N;  // double-buffered across tiles
-      for (int i = et; i < p.bb * BLOCK_N; i += kEpiThreads) {
-        const int sg = i / BLOCK_N, c = i % BLOCK_N;
-        const int n = n0 + c, bgl = b0 + sg;
-        float bv = 0.f;
-        if (n < p.N) {
-          if (p.bias && !p.bias_on_m) bv += __ldg(p.bias + n);
-          if (p.rowbias && bgl < p.Bn) bv += __ldg(p.rowbias + static_cast<long long>(bgl) * p.rowbias_ld + n);
+      // stage bias + per-sample (time-embedding) bias of this tile's columns, s_bias[seg][col] -- only when the tile's
+      // (column block, first sample) differs from what is already staged (for a conv that is once per sample)
+      const int bkey = p.rowbias ? b0 : 0;  // without a per-sample bias the staged values do not depend on the sample
+      if (n0 != staged_n0 || bkey != staged_b0) {
+        staged_n0 = n0; staged_b0 = bkey;
+        bias_buf ^= 1;  // the other buffer may still be read by warps finishing the previous tile
+        float* wb = s_stats + 16 * BLOCK_N + bias_buf * 4 * BLOCK_N;
+        for (int i = et; i < p.bb * BLOCK_N; i += kEpiThreads) {
+          const int sg = i / BLOCK_N, c = i % BLOCK_N;
+          const int n = n0 + c, bgl = b0 + sg;
+          float bv = 0.f;
+          if (n < p.N) {
+            if (p.bias && !p.bias_on_m) bv += __ldg(p.bias + n);
+            if (p.rowbias && bgl < p.Bn) bv += __ldg(p.rowbias + static_cast<long long>(bgl) * p.rowbias_ld + n);
+          }
+          wb[i] = bv;
         }
-        s_bias[i] = bv;
+        named_bar_sync(1, kEpiThreads);
       }
-      named_bar_sync(1, kEpiThreads);  // also orders the previous tile's statistics reads before this tile's writes
+      const float* s_bias = s_stats + 16 * BLOCK_N + bias_buf * 4 * BLOCK_N;
+      float* s_part = s_stats + (it & 1) * 8 * BLOCK_N;  // column partials, double-buffered across tiles
       // residual rows do not depend on the accumulator: fetch the first chunk while waiting for the MMAs, and every
       // next chunk while the current one is being stored, so the (L2/HBM) latency is never exposed
       uint4 rbuf[8];
@@ -519,11 +528,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
           }
           // per-warp slot, no atomics: the cross-warp sum below runs in a fixed order (deterministic results)
-          s_stats[(q * 2 + 0) * BLOCK_N + ch * 32 + lane] = s[0];
-          s_stats[(q * 2 + 1) * BLOCK_N + ch * 32 + lane] = ss[0];
+          s_part[(q * 2 + 0) * BLOCK_N + ch * 32 + lane] = s[0];
+          s_part[(q * 2 + 1) * BLOCK_N + ch * 32 + lane] = ss[0];
         }
       }
       if (p.stats) {
+        // the only barrier per tile: partials of tile i+1 go to the other buffer, and a buffer is rewritten two tiles
+        // later, after every warp has passed this barrier once more
         named_bar_sync(1, kEpiThreads);
         const int warps_per_seg = rows_per_b >= 128 ? 4 : rows_per_b / 32;
         for (int i = et; i < p.bb * BLOCK_N; i += kEpiThreads) {
@@ -532,8 +543,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (bgl < p.Bn && n < p.N) {
             float ts = 0.f, tq = 0.f;
             for (int w = sg * warps_per_seg; w < (sg + 1) * warps_per_seg; ++w) {
-              ts += s_stats[(w * 2 + 0) * BLOCK_N + c];
-              tq += s_stats[(w * 2 + 1) * BLOCK_N + c];
+              ts += s_part[(w * 2 + 0) * BLOCK_N + c];
+              tq += s_part[(w * 2 + 1) * BLOCK_N + c];
             }
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.stats) + (static_cast<long long>(bgl) * p.N + n) * 2;
             atomicAdd(dst, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(ts) * 16777216.0)));
