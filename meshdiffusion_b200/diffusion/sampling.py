@@ -63,6 +63,10 @@ def get_sampling_fn(config, sde, shape, inverse_scaler, eps, grid_mask=None, ret
             return_traj=return_traj,
             max_iters=config.sampling.get("max_iters", None), native_rng=config.sampling.get("native_rng", False),
             seed=config.get("seed", 42))
+    if method == "ddim":
+        return get_ddim_sampler(sde=sde, shape=shape, predictor=get_predictor("ddim"), inverse_scaler=inverse_scaler,
+                                n_steps=config.sampling.n_steps_each, denoise=config.sampling.noise_removal, eps=eps,
+                                device=config.device, grid_mask=grid_mask)
     raise ValueError(f"Sampler name {method} unknown.")
 
 
@@ -323,3 +327,58 @@ def _native_loop(net, x, mask_flat, labels, betas, stds, total, seed):
                                     arr(betas), arr(stds), total, B, int(seed), _native.ptr(eps_buf),
                                     _native.ptr(labels_buf), _native.current_stream()))
     return x_mean
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DDIM (deterministic) sampling. The reference registers a 'ddim' predictor (sampling.py:249-257) on top of
+# RSDE.discretize_ddim (sde_lib.py:113-140) and ships get_ddim_sampler (sampling.py:500-570), whose last line raises a
+# NameError (`encode` is undefined). The update below is the same fp64 arithmetic; the sampler is the working version.
+@register_predictor(name="ddim")
+class DDIMPredictor(Predictor):
+    def update_fn(self, x, t, tprev=None):
+        sde = self.sde
+        step = (t * (sde.N - 1) / sde.T).long()
+        step_prev = (tprev * (sde.N - 1) / sde.T).long()
+        eps = self.score_fn(x.float(), t.float())  # std_scale=False: the raw noise prediction
+        a1 = _bcast(sde.sqrt_alphas_cumprod.to(x.device)[step])
+        a2 = _bcast(sde.sqrt_1m_alphas_cumprod.to(x.device)[step])
+        a1p = _bcast(sde.sqrt_alphas_cumprod.to(x.device)[step_prev])
+        a2p = _bcast(sde.sqrt_1m_alphas_cumprod.to(x.device)[step_prev])
+        r1 = a1p.double() / a1.double()
+        r2 = a2p.double() / a2.double()
+        x0_scaled = x.double() - a2.double() * eps.double()
+        noise_part = x - x0_scaled
+        x0_pred = x0_scaled / a1
+        x_new = r1 * x + (-r1 + r2) * noise_part.double()
+        return x_new, x0_pred
+
+
+def get_ddim_sampler(sde, shape, predictor, inverse_scaler, n_steps=1, denoise=False, eps=1e-3, device="cuda",
+                     grid_mask=None):
+    def ddim_sampler(model, schedule="quad", num_steps=100, x0=None, partial=None, partial_mask=None, partial_channel=0):
+        with torch.no_grad():
+            x = (x0 if x0 is not None else sde.prior_sampling(shape).to(device)) * grid_mask
+            c = partial_channel
+            if partial is not None:
+                x[:, c] = x[:, c] * (1 - partial_mask) + partial * partial_mask
+            if schedule == "uniform":
+                seq = list(range(0, sde.N, sde.N // num_steps))
+            elif schedule == "quad":
+                seq = [int(s) for s in np.linspace(0, np.sqrt(sde.N * 0.8), 100) ** 2]
+            else:
+                raise ValueError(f"unknown DDIM schedule {schedule}")
+            timesteps = torch.tensor(seq) / sde.N
+            score_fn = mutils.get_score_fn(sde, model, train=False, continuous=False, std_scale=False)
+            pred = (predictor or DDIMPredictor)(sde, score_fn, False)
+            x0_pred = x
+            for i in reversed(range(1, len(timesteps))):
+                vec_t = torch.ones(shape[0], device=device) * timesteps[i].to(device)
+                vec_tprev = torch.ones(shape[0], device=device) * timesteps[i - 1].to(device)
+                x, x0_pred = pred.update_fn(x, vec_t, vec_tprev)
+                x, x0_pred = (x * grid_mask).float(), (x0_pred * grid_mask).float()
+                if partial is not None:
+                    x[:, c] = x[:, c] * (1 - partial_mask) + partial * partial_mask
+                    x0_pred[:, c] = x0_pred[:, c] * (1 - partial_mask) + partial * partial_mask
+            return inverse_scaler(x0_pred * grid_mask if denoise else x * grid_mask), sde.N * (n_steps + 1)
+
+    return ddim_sampler

@@ -50,11 +50,14 @@ class FusedAdamEMA:
             _native.check(L.mdb_grad_clip_coef(_native.ptr(grads), _native.ptr(self._numels), n, float(max_norm),
                                                _native.ptr(self._coef), _native.ptr(self._norm), _native.ptr(self._scratch), stream))
             coef = self._coef
-        ema_tab = self._table(self.ema) if self.ema is not None else None
-        _native.check(L.mdb_adam_ema_step(_native.ptr(self._table(self.params)), _native.ptr(grads),
-                                          _native.ptr(self._table(self.exp_avg)), _native.ptr(self._table(self.exp_avg_sq)),
-                                          _native.ptr(ema_tab), _native.ptr(self._numels), n,
+        # the pointer tables must stay alive until the kernel has been enqueued (torch's allocator would otherwise hand
+        # the same block to the next table)
+        t_ema = self._table(self.ema) if self.ema is not None else None
+        t_p, t_m, t_v = self._table(self.params), self._table(self.exp_avg), self._table(self.exp_avg_sq)
+        _native.check(L.mdb_adam_ema_step(_native.ptr(t_p), _native.ptr(grads), _native.ptr(t_m), _native.ptr(t_v),
+                                          _native.ptr(t_ema), _native.ptr(self._numels), n,
                                           float(self.lr if lr is None else lr), self.betas[0], self.betas[1], self.eps,
                                           self.step_count, _native.ptr(coef),
                                           float(self.ema_decay if ema_decay is None else ema_decay), stream))
+        self._keepalive = (t_p, t_m, t_v, t_ema, grads)
         return self._norm

@@ -134,9 +134,21 @@ def golden_sampler(ref):
         cerr = (c_ref - c_orc).abs().max().item()
         print(f"sampler partial ({n_it} iters): oracle-vs-reference max abs diff {cerr:.3e}")
         assert cerr <= 1e-4
+        # DDIM update (the reference's predictor works; only its sampler's return statement is broken)
+        rscore = ref["rutils"].get_score_fn(sde, model, train=False, continuous=False, std_scale=False)
+        g = torch.Generator().manual_seed(51)
+        xd = torch.randn(B, 4, R, R, R, generator=g) * grid_mask
+        td, tp = torch.full((B,), 0.64), torch.full((B,), 0.6084)
+        with torch.no_grad():
+            d_ref = sde.reverse(rscore, False).discretize_ddim(xd, td, tprev=tp)
+            d_orc = sampler_oracle.ddim_update(osde, fn, xd, td, tp)
+        derr = max((d_ref[0] - d_orc[0]).abs().max().item(), (d_ref[1] - d_orc[1]).abs().max().item())
+        print(f"ddim update: oracle-vs-reference max abs diff {derr:.3e}")
+        assert derr <= 1e-4
     finally:
         rsamp.tqdm.trange = real_trange
     np.savez_compressed(os.path.join(GOLD, "sampler_tiny.npz"), uncond=s_ref.numpy(), partial=c_ref.numpy(),
+                        ddim_x=d_ref[0].numpy(), ddim_x0=d_ref[1].numpy(),
                         checksum=synth.state_checksum(sd), state_seed=21, n_iters=n_it,
                         betas=sde.discrete_betas.numpy(), sqrt_1m_ac=sde.sqrt_1m_alphas_cumprod.numpy())
 

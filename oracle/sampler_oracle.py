@@ -94,3 +94,22 @@ def pc_sample_partial(sde, model, x_init, grid_mask, partial, partial_mask, nois
             x[:, c] = (x[:, c] * (1 - partial_mask[:, c]) + sampled * partial_mask[:, c]) * grid_mask[:, c]
             x_mean[:, c] = x[:, c]
     return x_mean if denoise else x
+
+
+def ddim_update(sde, model, x, t, tprev):
+    """RSDE.discretize_ddim (lib/diffusion/sde_lib.py:113-140) with score_fn = raw noise prediction
+    (get_score_fn(..., std_scale=False), models/utils.py:186-190): fp64 update, returns (x_new, x0_pred)."""
+    step = (t * (sde.N - 1) / sde.T).long()
+    step_prev = (tprev * (sde.N - 1) / sde.T).long()
+    eps = model(x.float(), t.float() * (sde.N - 1))
+    a1 = sde.sqrt_alphas_cumprod[step][:, None, None, None, None]
+    a2 = sde.sqrt_1m_alphas_cumprod[step][:, None, None, None, None]
+    a1p = sde.sqrt_alphas_cumprod[step_prev][:, None, None, None, None]
+    a2p = sde.sqrt_1m_alphas_cumprod[step_prev][:, None, None, None, None]
+    r1 = a1p.double() / a1.double()
+    r2 = a2p.double() / a2.double()
+    x0_scaled = x.double() - a2.double() * eps.double()
+    noise_part = x - x0_scaled
+    x0_pred = x0_scaled / a1
+    x_new = r1.double() * x + (-r1 + r2.double()) * noise_part.double()
+    return x_new, x0_pred

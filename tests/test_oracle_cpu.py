@@ -67,3 +67,16 @@ def test_grid_mask_from_tets_has_reference_population():
     m = dmtet.grid_mask_from_tets(64)
     assert int(m.sum()) == 30512 and m.shape == (64, 64, 64)  # 30 512 of 262 144 voxels
     assert int(dmtet.grid_mask_from_tets(128).sum()) == 253024
+
+
+def test_ddim_oracle_matches_reference_golden():
+    gold = load_golden("sampler_tiny.npz")
+    cfg, sd = _tiny_sd("res64", int(gold["state_seed"]))
+    R, B = 16, 2
+    sde = sampler_oracle.VPSDETables(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales)
+    fn = lambda x, t: unet_oracle.unet_forward(sd, unet_oracle.arch_from_config(cfg), x, t)
+    g = torch.Generator().manual_seed(51)
+    xd = torch.randn(B, 4, R, R, R, generator=g) * sd["mask"].view(1, R, R, R)
+    with torch.no_grad():
+        xn, x0 = sampler_oracle.ddim_update(sde, fn, xd, torch.full((B,), 0.64), torch.full((B,), 0.6084))
+    assert np.abs(xn.numpy() - gold["ddim_x"]).max() < 2e-4 and np.abs(x0.numpy() - gold["ddim_x0"]).max() < 2e-4
