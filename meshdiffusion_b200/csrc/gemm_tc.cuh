@@ -141,7 +141,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // no data is published with this arrival (it only hands a TMEM stage back; tcgen05.fence orders the TMEM reads), so
+  // the default cta-scope release is enough -- a cluster-scope release costs a full memory barrier per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_5d_cg2(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
