@@ -173,64 +173,70 @@ void launch_upsample2x(const void* x, void* y, int B, int Z, int Y, int X, int C
 }
 
 // ------------------------------------------------------------------ stem im2col
-// One block per (sample, z, y) row of the output: the k*k input rows it needs are staged in shared memory once,
-// then every thread emits 16-byte vectors of the [voxel][Kpad] operand matrix (column = cin*k^3 + tap).
+// One block per (sample, z, group of YB y-rows): the k x (k+YB-1) input rows it needs are staged in shared memory once
+// (a warp per row, no per-element div/mod), then every thread emits 16-byte vectors of the [voxel][Kpad] operand
+// matrix (column = cin*k^3 + tap) through a per-column slab-offset table.
+constexpr int kIm2colYB = 4;
 template <bool TF32>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, void* __restrict__ a, int Cin, int R, int k, int Kpad) {
   constexpr int VEC = TF32 ? 4 : 8;
-  extern __shared__ float slab[];  // [Cin][k][k][R + 2*pad]
-  const int pad = k / 2, W = R + 2 * pad, T = k * k * k;
-  const int y0 = blockIdx.x % R, z0 = (blockIdx.x / R) % R, b = blockIdx.x / (R * R);
+  constexpr int YB = kIm2colYB;
+  extern __shared__ float slab[];  // [Cin][k][k+YB-1][R + 2*pad]
+  const int pad = k / 2, W = R + 2 * pad, T = k * k * k, KH = k + YB - 1;
+  const int yblocks = R / YB;
+  const int y0 = (blockIdx.x % yblocks) * YB, z0 = (blockIdx.x / yblocks) % R, b = blockIdx.x / (yblocks * R);
   const long long V = (long long)R * R * R;
-  const int slab_n = Cin * k * k * W;
-  for (int i = threadIdx.x; i < slab_n; i += blockDim.x) {
-    int r = i;
-    const int xw = r % W; r /= W;
-    const int kh = r % k; r /= k;
-    const int kd = r % k; r /= k;
-    const int ci = r;
-    const int zi = z0 + kd - pad, yi = y0 + kh - pad, xi = xw - pad;
-    float v = 0.f;
-    if (zi >= 0 && zi < R && yi >= 0 && yi < R && xi >= 0 && xi < R)
-      v = __ldg(x + ((long long)b * Cin + ci) * V + ((long long)zi * R + yi) * R + xi);
-    slab[i] = v;
+  const int n_rows = Cin * k * KH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < n_rows; row += 8) {
+    const int khh = row % KH, kd = (row / KH) % k, ci = row / (KH * k);
+    const int zi = z0 + kd - pad, yi = y0 + khh - pad;
+    const bool row_ok = zi >= 0 && zi < R && yi >= 0 && yi < R;
+    const float* src = x + ((long long)b * Cin + ci) * V + ((long long)zi * R + yi) * R;
+    for (int xw = lane; xw < W; xw += 32) {
+      const int xi = xw - pad;
+      slab[row * W + xw] = (row_ok && xi >= 0 && xi < R) ? __ldg(src + xi) : 0.f;
+    }
   }
-  // slab offset of every operand column (independent of x): removes all div/mod from the emit loop
-  int* coloff = reinterpret_cast<int*>(slab + slab_n);
+  int* coloff = reinterpret_cast<int*>(slab + n_rows * W);
   for (int col = threadIdx.x; col < Kpad; col += blockDim.x) {
     int off = -1;
     if (col < Cin * T) {
       const int ci = col / T, tap = col % T;
       const int kd = tap / (k * k), kh = (tap / k) % k, kw = tap % k;
-      off = ((ci * k + kd) * k + kh) * W + kw;
+      off = ((ci * k + kd) * KH + kh) * W + kw;
     }
     coloff[col] = off;
   }
   __syncthreads();
   const int kv = Kpad / VEC;
-  const long long row0 = (((long long)b * R + z0) * R + y0) * R;
-  for (int i = threadIdx.x; i < R * kv; i += blockDim.x) {
-    const int xo = i / kv, col0 = (i - xo * kv) * VEC;
-    float v[VEC];
+  for (int yb = 0; yb < YB; ++yb) {
+    const long long row0 = (((long long)b * R + z0) * R + y0 + yb) * R;
+    const int ybase = yb * W;
+    for (int i = threadIdx.x; i < R * kv; i += blockDim.x) {
+      const int xo = i / kv, col0 = (i - xo * kv) * VEC;
+      float v[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int off = coloff[col0 + j];
-      v[j] = off >= 0 ? slab[off + xo] : 0.f;
-    }
-    if (TF32) {
-      *((float4*)((float*)a + (row0 + xo) * Kpad + col0)) =
-          make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
-    } else {
-      uint4 t;
-      __nv_bfloat162* h = (__nv_bfloat162*)&t;
+      for (int j = 0; j < VEC; ++j) {
+        const int off = coloff[col0 + j];
+        v[j] = off >= 0 ? slab[off + ybase + xo] : 0.f;
+      }
+      if (TF32) {
+        *((float4*)((float*)a + (row0 + xo) * Kpad + col0)) =
+            make_float4(round_tf32_rna(v[0]), round_tf32_rna(v[1]), round_tf32_rna(v[2]), round_tf32_rna(v[3]));
+      } else {
+        uint4 t;
+        __nv_bfloat162* h = (__nv_bfloat162*)&t;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * Kpad + col0)) = t;
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * Kpad + col0)) = t;
+      }
     }
   }
 }
 void launch_im2col(const float* x, void* a, int B, int Cin, int R, int k, int Kpad, int tf32, cudaStream_t s) {
-  const size_t smem = (size_t)Cin * k * k * (R + 2 * (k / 2)) * sizeof(float) + (size_t)Kpad * sizeof(int);
+  if (R % kIm2colYB != 0) throw std::runtime_error("mdb: im2col needs a grid size divisible by 4");
+  const size_t smem = (size_t)Cin * k * (k + kIm2colYB - 1) * (R + 2 * (k / 2)) * sizeof(float) + (size_t)Kpad * sizeof(int);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(im2col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -238,7 +244,7 @@ void launch_im2col(const float* x, void* a, int B, int Cin, int R, int k, int Kp
     configured = true;
   }
   if (smem > 100 * 1024) throw std::runtime_error("mdb: im2col slab too large");
-  const unsigned grid = (unsigned)(B * R * R);
+  const unsigned grid = (unsigned)(B * R * (R / kIm2colYB));
   if (tf32) im2col_kernel<true><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
   else im2col_kernel<false><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
   MDB_LAUNCH_CHECK();

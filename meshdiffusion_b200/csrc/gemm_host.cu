@@ -96,6 +96,7 @@ void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N,
   p.N = N;
   block_n = N <= 32 ? 32 : 128;
   p.n_tiles_n = (N + block_n - 1) / block_n;
+  { const char* f = getenv("MDB_DBG_FLAGS"); p.dbg_flags = f ? atoi(f) : 0; }
   {
     // CTA pairs (tcgen05 cta_group::2) whenever there are enough M-tiles to keep all 74 pairs busy
     const char* e = getenv("MDB_CTA_PAIRS");

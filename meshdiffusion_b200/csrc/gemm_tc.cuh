@@ -71,6 +71,7 @@ struct GemmParams {
   int n_tiles_n;
   int N;               // valid output columns
   int b_batched;       // B tensor map has a batch coordinate following the tile's sample
+  int dbg_flags;       // experiment switches (bit 0: cluster-scope release on the remote t_empty arrive)
   int batch_fastest;   // enumerate the batch axis first among M-tiles (residual shared by all samples stays in L2)
   int kb_elems;        // K elements per k-step (64 bf16 / 32 tf32)
   // epilogue
@@ -144,6 +145,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // no data is published with this arrival (it only hands a TMEM stage back; tcgen05.fence orders the TMEM reads), so
   // the default cta-scope release is enough -- a cluster-scope release costs a full memory barrier per tile
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_5d_cg2(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (!active) {  // nothing to drain for this warp: still release its share of the TMEM stage
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive(t_empty + 8 * acc); }
+        if (lane == 0) { if constexpr (CG2) { if (p.dbg_flags & 1) mbar_arrive_cluster_release(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); } else mbar_arrive(t_empty + 8 * acc); }
       }
       for (int ch = ch0; ch < kChunks && active; ch += kChunkStep) {
         uint32_t rr[32];
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive(t_empty + 8 * acc); }
+          if (lane == 0) { if constexpr (CG2) { if (p.dbg_flags & 1) mbar_arrive_cluster_release(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); } else mbar_arrive(t_empty + 8 * acc); }
         }
         const int nb = n0 + ch * 32;
         if (nb >= p.N) continue;  // warp-uniform
