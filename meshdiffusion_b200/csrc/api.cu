@@ -201,20 +201,12 @@ int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma,
                       long long V, int C, int silu, int precision, void* stream) {
   MDB_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
-  float *scale = nullptr, *shift = nullptr;
-  MDB_CUDA_CHECK(cudaMalloc(&scale, (size_t)B * C * 4));
-  MDB_CUDA_CHECK(cudaMalloc(&shift, (size_t)B * C * 4));
-  GnFinalizeArgs fa{};
-  fa.stats0 = stats; fa.C0 = C; fa.stats1 = nullptr; fa.C1 = 0; fa.gamma = gamma; fa.beta = beta;
-  fa.scale = scale; fa.shift = shift; fa.groups = 32; fa.eps = 1e-6f; fa.count_per_channel = (double)V;
-  launch_gn_finalize(fa, B, s);
   NormActArgs na{};
-  na.x0 = x; na.C0 = C; na.ld0 = C; na.x1 = nullptr; na.C1 = 0; na.ld1 = 0; na.scale = scale; na.shift = shift;
+  na.x0 = x; na.C0 = C; na.ld0 = C; na.x1 = nullptr; na.C1 = 0; na.ld1 = 0; na.scale = nullptr; na.shift = nullptr;
   na.y = y; na.voxels = V; na.silu = silu; na.tf32 = precision ? 1 : 0;
+  na.stats0 = stats; na.stats1 = nullptr; na.gamma = gamma; na.beta = beta; na.groups = 32; na.eps = 1e-6f;
   launch_norm_act(na, B, s);
   MDB_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(scale);
-  cudaFree(shift);
   MDB_API_END
 }
 

@@ -21,9 +21,13 @@ void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s);
 struct NormActArgs {
   const void* x0; int C0; long long ld0;
   const void* x1; int C1; long long ld1;
-  const float* scale; const float* shift;  // [B][C0+C1]
+  const float* scale; const float* shift;  // [B][C0+C1] (only when stats0 == nullptr: precomputed by gn_finalize)
   void* y;                                 // [B][V][C0+C1] dense
   long long voxels; int silu; int tf32;
+  // fused GroupNorm finalize: per-channel (sum, sumsq) of the two sources as 2^-24 fixed point, affine parameters
+  const long long* stats0; const long long* stats1;
+  const float* gamma; const float* beta;
+  int groups; float eps;
 };
 void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s);
 

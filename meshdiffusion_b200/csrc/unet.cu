@@ -126,19 +126,13 @@ TensP UNet::gn(const std::string& pname, const std::vector<TensP>& ins, bool sil
   float* beta = P(pname + ".bias", {C});
   TensP y = new_act(C, R, false);
   if (dry_) return y;
-  float* scale = (float*)dmalloc((size_t)cfg_.max_batch * C * 4);
-  float* shift = (float*)dmalloc((size_t)cfg_.max_batch * C * 4);
-  GnFinalizeArgs fa{};
-  fa.stats0 = ins[0]->stats; fa.C0 = ins[0]->C;
-  fa.stats1 = ins.size() > 1 ? ins[1]->stats : nullptr; fa.C1 = ins.size() > 1 ? ins[1]->C : 0;
-  fa.gamma = gamma; fa.beta = beta; fa.scale = scale; fa.shift = shift;
-  fa.groups = 32; fa.eps = 1e-6f; fa.count_per_channel = (double)R * R * R;
   NormActArgs na{};
   na.x0 = ins[0]->ptr; na.C0 = ins[0]->C; na.ld0 = ins[0]->C;
-  na.x1 = ins.size() > 1 ? ins[1]->ptr : nullptr; na.C1 = fa.C1; na.ld1 = fa.C1;
-  na.scale = scale; na.shift = shift; na.y = y->ptr; na.voxels = (long long)R * R * R; na.silu = silu ? 1 : 0;
+  na.x1 = ins.size() > 1 ? ins[1]->ptr : nullptr; na.C1 = ins.size() > 1 ? ins[1]->C : 0; na.ld1 = na.C1;
+  na.scale = nullptr; na.shift = nullptr; na.y = y->ptr; na.voxels = (long long)R * R * R; na.silu = silu ? 1 : 0;
   na.tf32 = prec_ == kTF32;
-  add_step("gn_finalize:" + pname, [fa](cudaStream_t s, int B) { launch_gn_finalize(fa, B, s); });
+  na.stats0 = ins[0]->stats; na.stats1 = ins.size() > 1 ? ins[1]->stats : nullptr;
+  na.gamma = gamma; na.beta = beta; na.groups = 32; na.eps = 1e-6f;
   add_step("norm_act:" + pname, [na](cudaStream_t s, int B) { launch_norm_act(na, B, s); });
   return y;
 }
