@@ -451,6 +451,47 @@ void launch_tap_shift_sum(const void* P, long long ldp, int p_fp32, const float*
   MDB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------ split-K reduction
+// blockIdx.y = sample, blockIdx.x = chunk of voxels; thread = output channel (coalesced rows). Each thread owns a
+// channel for its chunk, so its statistics are accumulated in a fixed order (deterministic) and published with one
+// integer atomic per (block, channel).
+template <bool TF32>
+__global__ void __launch_bounds__(256) split_reduce_kernel(SplitReduceArgs a, int vchunk) {
+  const int b = blockIdx.y;
+  const long long v0 = (long long)blockIdx.x * vchunk;
+  const long long v1 = v0 + vchunk < a.voxels ? v0 + vchunk : a.voxels;
+  for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
+    float add = a.bias ? a.bias[n] : 0.f;
+    if (a.rowbias) add += a.rowbias[(long long)b * a.rowbias_ld + n];
+    float s1 = 0.f, s2 = 0.f;
+    for (long long v = v0; v < v1; ++v) {
+      const long long idx = ((long long)b * a.voxels + v) * a.N + n;
+      float acc = add;
+      for (int sp = 0; sp < a.splits; ++sp) acc += a.partial[sp * a.split_stride + idx];
+      if (a.res) {
+        const long long ridx = (long long)b * a.res_batch_stride + v * a.N + n;
+        acc += TF32 ? ((const float*)a.res)[ridx] : __bfloat162float(((const __nv_bfloat16*)a.res)[ridx]);
+      }
+      s1 += acc; s2 += acc * acc;
+      if (TF32) ((float*)a.out)[idx] = round_tf32_rna(acc);
+      else ((__nv_bfloat16*)a.out)[idx] = __float2bfloat16(acc);
+    }
+    if (a.stats) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.stats) + ((long long)b * a.N + n) * 2;
+      atomicAdd(dst, (unsigned long long)__double2ll_rn((double)s1 * 16777216.0));
+      atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)s2 * 16777216.0));
+    }
+  }
+}
+void launch_split_reduce(const SplitReduceArgs& a, int B, cudaStream_t s) {
+  const int vchunk = 8;
+  dim3 grid((unsigned)((a.voxels + vchunk - 1) / vchunk), (unsigned)B);
+  const int threads = a.N < 256 ? ((a.N + 31) / 32) * 32 : 256;
+  if (a.tf32) split_reduce_kernel<true><<<grid, threads, 0, s>>>(a, vchunk);
+  else split_reduce_kernel<false><<<grid, threads, 0, s>>>(a, vchunk);
+  MDB_LAUNCH_CHECK();
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] + (b ? b[i] : 0.f);
 }

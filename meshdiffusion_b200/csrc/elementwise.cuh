@@ -55,6 +55,16 @@ void launch_dense(const float* x, const float* w, const float* bias, float* out,
 void launch_tap_shift_sum(const void* P, long long ldp, int p_fp32, const float* bias, float* out, int B, int R, int k,
                           int Cout, cudaStream_t s);
 
+// Split-K reduction + the GEMM epilogue terms: out[b][v][n] = sum_s partial[s][b][v][n] + bias[n] + rowbias[b][n] +
+// res[b][v][n], stored in the activation dtype, with the per-(sample, channel) GroupNorm statistics.
+struct SplitReduceArgs {
+  const float* partial; long long split_stride; int splits;
+  const float* bias; const float* rowbias; long long rowbias_ld;
+  const void* res; long long res_batch_stride;  // same [V][N] layout as out (activation dtype)
+  void* out; long long* stats; long long voxels; int N; int tf32;
+};
+void launch_split_reduce(const SplitReduceArgs& a, int B, cudaStream_t s);
+
 void launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
 
 // Ancestral-sampling predictor update fused with the score scaling and both mask multiplies

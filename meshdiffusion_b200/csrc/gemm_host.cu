@@ -1,5 +1,6 @@
 // Host-side builders for the tcgen05 implicit-GEMM kernel (see gemm_tc.cuh).
 #include "gemm_host.h"
+#include "elementwise.cuh"
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
@@ -74,6 +75,30 @@ Geometry pick_geometry(int X, int Y, int Z) {
   int bz = rem < Z ? rem : Z;
   int bb = rem / bz;
   return {bx, by, bz, bb};
+}
+
+int plan_splits(int X, int Y, int Z, int B, int N, int cin_total, int taps, Precision prec) {
+  const Geometry g = pick_geometry(X, Y, Z);
+  const int tiles_m = ((X + g.bx - 1) / g.bx) * ((Y + g.by - 1) / g.by) * ((Z + g.bz - 1) / g.bz) * ((B + g.bb - 1) / g.bb);
+  const int block_n = N <= 32 ? 32 : 128;
+  const int tiles = tiles_m * ((N + block_n - 1) / block_n);
+  const int ksteps = ((cin_total + kb_elems(prec) - 1) / kb_elems(prec)) * taps;
+  if (tiles > 37 || ksteps < 48) return 1;
+  int S = 148 / tiles;
+  if (S > 8) S = 8;
+  if (S > ksteps / 12) S = ksteps / 12;
+  return S < 2 ? 1 : S;
+}
+
+void GemmOp::enable_splits(int S, float* scratch) {
+  if (S <= 1) return;
+  if (pair || p.ocs != 1 || p.out_fp32 || p.bias_on_m || p.alpha != 1.f || p.res_fp32)
+    throw std::runtime_error("mdb: split-K is only wired for plain NDHWC conv outputs");
+  if (p.osx != p.N || (p.res && p.rsx != p.N)) throw std::runtime_error("mdb: split-K needs dense [B][V][N] output / residual");
+  splits = S;
+  p.splits = S;
+  p.partial = scratch;
+  p.split_stride = (long long)p.Bn * p.X * p.Y * p.Z * p.N;
 }
 
 GemmOp::~GemmOp() {
@@ -320,6 +345,7 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   MDB_CUDA_CHECK(cudaMemcpyAsync(d_loads, loads.data(), loads.size() * sizeof(LoadEntry), cudaMemcpyHostToDevice, stream));
   p.loads = d_loads;
   p.n_loads = (int)loads.size();
+  if (p.splits < 1) p.splits = 1;
   // pipeline segments: runs of identical entries; plain (nk == 1) entries are paired two per stage
   {
     const int btile = block_n * kRowBytes / (pair ? 2 : 1);
@@ -335,7 +361,9 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
       sg.jbytes = e.jrows * kRowBytes;
       if (epg * (sg.a_stride + e.nk * btile) > stage_bytes) throw std::runtime_error("mdb: pipeline group exceeds the stage size");
       p.segs[p.n_segs++] = sg;
+      p.total_groups += n_groups;
     };
+    p.total_groups = 0;
     size_t i = 0;
     while (i < loads.size()) {
       size_t j = i;
@@ -350,6 +378,7 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
       i = j;
     }
   }
+  if (p.splits > p.total_groups) { p.splits = p.total_groups; splits = p.splits; }
   if (!b_from_act) {
     const long long ktot = 1LL * ksteps * kb_elems(prec);
     const long long bytes = ktot * p.N * esize(prec);
@@ -405,10 +434,18 @@ void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
     if (tf) launch_impl<128, true, true>(p, grid, stream); else launch_impl<128, false, true>(p, grid, stream);
     return;
   }
-  const int total = tiles_m * p.n_tiles_n;
+  const int total = tiles_m * p.n_tiles_n * (p.splits > 1 ? p.splits : 1);
   int grid = total < sm_count() ? total : sm_count();
   if (block_n == 32) { if (tf) launch_impl<32, true, false>(p, grid, stream); else launch_impl<32, false, false>(p, grid, stream); }
   else { if (tf) launch_impl<128, true, false>(p, grid, stream); else launch_impl<128, false, false>(p, grid, stream); }
+  if (p.splits > 1) {
+    SplitReduceArgs a{};
+    a.partial = p.partial; a.split_stride = p.split_stride; a.splits = p.splits;
+    a.bias = p.bias; a.rowbias = p.rowbias; a.rowbias_ld = p.rowbias_ld;
+    a.res = p.res; a.res_batch_stride = p.rsb;
+    a.out = p.out; a.stats = p.stats; a.voxels = (long long)p.X * p.Y * p.Z; a.N = p.N; a.tf32 = tf ? 1 : 0;
+    launch_split_reduce(a, p.Bn, stream);
+  }
 }
 
 }  // namespace mdb

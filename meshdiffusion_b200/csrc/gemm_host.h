@@ -51,6 +51,7 @@ class GemmOp {
   Precision prec = kBF16;
   int block_n = 128;
   bool pair = false;  // CTA-pair kernel (cta_group::2)
+  int splits = 1;     // split-K factor (small problems: few tiles, long K)
   std::vector<LoadEntry> loads;
   std::vector<WSrc> wsrcs;
   int n_amaps = 0;
@@ -94,6 +95,8 @@ class GemmOp {
   void set_residual(const void* res, long long ldr, long long batch_stride, bool fp32);
   void set_stats(long long* stats) { p.stats = stats; }
   void set_alpha(float a) { p.alpha = a; }
+  // Split-K over `S` CTAs per tile; `scratch` holds S fp32 copies of the output ([B][V][N] each). Call before finalize.
+  void enable_splits(int S, float* scratch);
 
   // Packs weights (device gather kernel), uploads the table, encodes the B map. Call after all add_* calls.
   void finalize(cudaStream_t stream, bool pack = true);
@@ -109,5 +112,7 @@ class GemmOp {
 };
 
 int sm_count();
+// Split-K factor for a conv-like op (pure function of the shapes, so the dry planning pass and the real pass agree).
+int plan_splits(int X, int Y, int Z, int B, int N, int cin_total, int taps, Precision prec);
 
 }  // namespace mdb

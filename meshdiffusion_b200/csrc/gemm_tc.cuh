@@ -71,6 +71,10 @@ struct GemmParams {
   int n_tiles_n;
   int N;               // valid output columns
   int b_batched;       // B tensor map has a batch coordinate following the tile's sample
+  int splits;          // split-K: each tile's group sequence is cut into `splits` ranges handled by different CTAs
+  int total_groups;    // sum of segs[].n_groups
+  float* partial;      // [splits][same layout as out] fp32 partial sums (splits > 1)
+  long long split_stride;
   int dbg_flags;       // experiment switches (bit 0: cluster-scope release on the remote t_empty arrive)
   int batch_fastest;   // enumerate the batch axis first among M-tiles (residual shared by all samples stays in L2)
   int kb_elems;        // K elements per k-step (64 bf16 / 32 tf32)
@@ -237,11 +241,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 
   const int tiles_m = p.tx * p.ty * p.tz * p.tb;
   // work items: (M-tile, N-tile) for a single CTA, (pair of adjacent M-tiles, N-tile) for a CTA pair
-  const int total_tiles = (CG2 ? (tiles_m + 1) / 2 : tiles_m) * p.n_tiles_n;
+  const int splits = (!CG2 && p.splits > 1) ? p.splits : 1;
+  const int total_tiles = (CG2 ? (tiles_m + 1) / 2 : tiles_m) * p.n_tiles_n * splits;
   const int first_tile = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
+  // split-K range of a work item: groups [lo, hi) of the tile's group sequence
+  auto split_range = [&](int item, int& lo, int& hi) {
+    const int sidx = item % splits;
+    lo = (int)((long long)p.total_groups * sidx / splits);
+    hi = (int)((long long)p.total_groups * (sidx + 1) / splits);
+  };
   auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0) {
+    tile /= splits;
     int nt = tile % p.n_tiles_n;
     int mt = tile / p.n_tiles_n;
     if (CG2) mt = 2 * mt + (int)rank;
@@ -265,13 +277,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       int x0, y0, z0, b0, n0;
       decode(tile, x0, y0, z0, b0, n0);
-      int kcol = 0, l = 0;
+      int kcol = 0, l = 0, gi = 0, g_lo, g_hi;
+      split_range(tile, g_lo, g_hi);
       const int bcoord = p.b_batched ? b0 : 0;
       for (int sg = 0; sg < p.n_segs; ++sg) {
         const GemmSeg seg = p.segs[sg];
         const uint32_t group_bytes = seg.epg * (seg.a_bytes + seg.nk * Cfg::kBTileBytes);
         const uint32_t b_base = seg.epg * seg.a_stride;
-        for (int g = 0; g < seg.n_groups; ++g) {
+        for (int g = 0; g < seg.n_groups; ++g, ++gi) {
+          if (gi < g_lo || gi >= g_hi) {  // another CTA's share of this tile's K range
+            kcol += seg.epg * seg.nk * p.kb_elems;
+            l += seg.epg;
+            continue;
+          }
           // the table entries of this group are fetched before blocking on the stage
           const uint4 raw0 = __ldg(reinterpret_cast<const uint4*>(p.loads + l));
           uint4 raw1 = raw0;
@@ -327,10 +345,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       uint32_t accumulate = 0;
+      int gi = 0, g_lo, g_hi;
+      split_range(tile, g_lo, g_hi);
       for (int sg = 0; sg < p.n_segs; ++sg) {
         const GemmSeg seg = p.segs[sg];
         const uint32_t b_base = seg.epg * seg.a_stride;
-        for (int g = 0; g < seg.n_groups; ++g) {
+        for (int g = 0; g < seg.n_groups; ++g, ++gi) {
+          if (gi < g_lo || gi >= g_hi) continue;
           mbar_wait(full + 8 * st, ph);
           tc_fence_after();
           if (elect_one()) {
@@ -446,6 +467,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         }
         const int nb = n0 + ch * 32;
         if (nb >= p.N) continue;  // warp-uniform
+        if (splits > 1) {
+          // split-K: raw fp32 partial sums; bias / residual / statistics are applied by the reduction kernel
+          if (valid) {
+            float* pp = p.partial + (long long)(tile % splits) * p.split_stride + ooff + nb;
+            if (nb + 32 <= p.N) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(pp)[i] = make_float4(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1]),
+                                                               __uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3]));
+            } else {
+              for (int i = 0; i < 32; ++i) if (nb + i < p.N) pp[i] = __uint_as_float(rr[i]);
+            }
+          }
+          continue;
+        }
         const bool full = (nb + 32 <= p.N) && (p.ocs == 1);
         float v[32];
         const float mbias = (p.bias && p.bias_on_m && valid) ? __ldg(p.bias + xg) : 0.f;
@@ -511,7 +547,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
           }
         }
-        if (p.stats) {
+        if (p.stats) {  // (never reached in split-K mode)
           // Column sums over the warp's 32 rows: butterfly transpose-reduce (31 shuffles per quantity);
           // afterwards lane i holds the sum of column i.
           float s[32], ss[32];
@@ -538,7 +574,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           s_part[(q * 2 + 1) * BLOCK_N + ch * 32 + lane] = ss[0];
         }
       }
-      if (p.stats) {
+      if (p.stats && splits == 1) {
         // the only barrier per tile: partials of tile i+1 go to the other buffer, and a buffer is rewritten two tiles
         // later, after every warp has passed this barrier once more
         named_bar_sync(1, kEpiThreads);

@@ -107,6 +107,24 @@ Act UNet::act_of(const TensP& t) const {
   return a;
 }
 
+// Split-K scratch for small problems (few output tiles, long K: the low-resolution levels at small batch). Decided
+// from shapes only so the dry sizing pass and the real pass make identical arena allocations.
+UNet::Scratch UNet::split_begin(int R, int N, int cin_total, int taps) {
+  Scratch s;
+  s.S = plan_splits(R, R, R, cfg_.max_batch, N, cin_total, taps, prec_);
+  if (s.S > 1) {
+    const size_t bytes = (size_t)s.S * cfg_.max_batch * R * R * R * N * sizeof(float);
+    s.off = arena_.alloc(bytes);
+    s.ptr = dry_ ? nullptr : reinterpret_cast<float*>(arena_base_ + s.off);
+    s.active = true;
+  }
+  return s;
+}
+void UNet::split_end(Scratch& s) {
+  if (s.active) arena_.release(s.off);
+  s.active = false;
+}
+
 GemmOp* UNet::new_gemm(const std::string& name, bool commit_time) {
   auto g = std::make_unique<GemmOp>();
   g->name = name;
@@ -155,6 +173,7 @@ TensP UNet::resblock(const std::vector<TensP>& ins, int out_ch, int midx) {
   P(pre + "Dense_0.bias", {out_ch}, dry_ ? nullptr : dense_b_ + doff);
   if (dry_) { params_[pindex_[pre + "Dense_0.weight"]].external = true; params_[pindex_[pre + "Dense_0.bias"]].external = true; }
   TensP h = new_act(out_ch, R, true);
+  Scratch sp0 = split_begin(R, out_ch, Cin, 27);
   if (!dry_) {
     GemmOp* g = new_gemm("res" + std::to_string(midx) + ".conv0");
     g->set_output(prec_, R, R, R, mb, out_ch, h->ptr, out_ch, false);
@@ -162,9 +181,11 @@ TensP UNet::resblock(const std::vector<TensP>& ins, int out_ch, int midx) {
     g->set_bias(b0);
     g->set_rowbias(dense_out_ + doff, dense_total_);
     g->set_stats(h->stats);
+    g->enable_splits(sp0.S, sp0.ptr);
     g->finalize(0, false);
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
+  split_end(sp0);
   release(a);
   TensP a2 = gn(pre + "GroupNorm_1", {h}, true);
   release(h);
@@ -178,6 +199,7 @@ TensP UNet::resblock(const std::vector<TensP>& ins, int out_ch, int midx) {
     throw std::runtime_error("mdb: identity shortcut over a concatenation is not supported");
   }
   TensP out = new_act(out_ch, R, true);
+  Scratch sp1 = split_begin(R, out_ch, out_ch, 27);
   if (!dry_) {
     GemmOp* g = new_gemm("res" + std::to_string(midx) + ".conv1");
     g->set_output(prec_, R, R, R, mb, out_ch, out->ptr, out_ch, false);
@@ -194,9 +216,11 @@ TensP UNet::resblock(const std::vector<TensP>& ins, int out_ch, int midx) {
       g->set_residual(ins[0]->ptr, out_ch, (long long)R * R * R * out_ch, false);
     }
     g->set_stats(out->stats);
+    g->enable_splits(sp1.S, sp1.ptr);
     g->finalize(0, false);
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
+  split_end(sp1);
   release(a2);
   return out;
 }
@@ -280,15 +304,18 @@ TensP UNet::downsample(const TensP& x, int midx) {
   float* w = P(pre + "Conv_0.weight", {C, C, 3, 3, 3});
   float* b = P(pre + "Conv_0.bias", {C});
   TensP out = new_act(C, R, true);
+  Scratch sp = split_begin(R, C, C, 27);
   if (!dry_) {
     GemmOp* g = new_gemm("down" + std::to_string(midx));
     g->set_output(prec_, R, R, R, cfg_.max_batch, C, out->ptr, C, false);
     g->add_conv({act_of(x)}, w, 3, 2);
     g->set_bias(b);
     g->set_stats(out->stats);
+    g->enable_splits(sp.S, sp.ptr);
     g->finalize(0, false);
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
+  split_end(sp);
   return out;
 }
 
@@ -303,15 +330,18 @@ TensP UNet::upsample(const TensP& x, int midx) {
     add_step("up" + std::to_string(midx) + ".nearest", [=](cudaStream_t s, int B) { launch_upsample2x(src, dst, B, r, r, r, C, tf, s); });
   }
   TensP out = new_act(C, R, true);
+  Scratch sp = split_begin(R, C, C, 27);
   if (!dry_) {
     GemmOp* g = new_gemm("up" + std::to_string(midx) + ".conv");
     g->set_output(prec_, R, R, R, cfg_.max_batch, C, out->ptr, C, false);
     g->add_conv({act_of(up)}, w, 3, 1);
     g->set_bias(b);
     g->set_stats(out->stats);
+    g->enable_splits(sp.S, sp.ptr);
     g->finalize(0, false);
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
+  split_end(sp);
   release(up);
   return out;
 }

@@ -112,6 +112,9 @@ class UNet {
   Act act_of(const TensP& t) const;
   GemmOp* new_gemm(const std::string& name, bool commit_time = false);
   void add_step(const std::string& name, std::function<void(cudaStream_t, int)> fn) { if (!dry_) steps_.push_back({name, fn}); }
+  struct Scratch { int S = 1; size_t off = 0; float* ptr = nullptr; bool active = false; };
+  Scratch split_begin(int R, int N, int cin_total, int taps);
+  void split_end(Scratch& s);
   TensP gn(const std::string& pname, const std::vector<TensP>& ins, bool silu);
   TensP resblock(const std::vector<TensP>& ins, int out_ch, int midx);
   TensP attn(const TensP& x, int midx);
