@@ -83,10 +83,10 @@ int plan_splits(int X, int Y, int Z, int B, int N, int cin_total, int taps, Prec
   const int block_n = N <= 32 ? 32 : 128;
   const int tiles = tiles_m * ((N + block_n - 1) / block_n);
   const int ksteps = ((cin_total + kb_elems(prec) - 1) / kb_elems(prec)) * taps;
-  if (tiles > 37 || ksteps < 48) return 1;
+  if (tiles > 49 || ksteps < 48) return 1;
   int S = 148 / tiles;
-  if (S > 8) S = 8;
-  if (S > ksteps / 12) S = ksteps / 12;
+  if (S > 16) S = 16;
+  if (S > ksteps / 8) S = ksteps / 8;
   return S < 2 ? 1 : S;
 }
 
