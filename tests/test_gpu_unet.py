@@ -79,3 +79,19 @@ def test_state_dict_roundtrip_and_mask_update():
     assert not torch.equal(a, b)
     model.module.mask.data[:] = sd["mask"].cuda()
     assert torch.equal(model(x, labels), a)
+
+
+def test_full_size_determinism_and_batch_invariance():
+    """BASELINE-size network (res64, batch 8 of the engine): two evaluations are bitwise identical (integer-atomic
+    GroupNorm statistics, fixed-order reductions), and a sample's result does not depend on its batch-mates."""
+    cfg = full_config("res64", "bf16")
+    cfg.model.engine_max_batch = 8
+    model, sd = build_model(cfg, "cuda:0", 5)
+    x, labels = synth.synthetic_inputs(64, 8, 7, sd["mask"])
+    x, labels = x.cuda(), labels.cuda()
+    a = model(x, labels)
+    b = model(x, labels)
+    assert torch.equal(a, b), "forward pass is not bitwise reproducible"
+    c = model(x[:3].contiguous(), labels[:3].contiguous())
+    assert torch.equal(a[:3], c), "a sample's output depends on the rest of the batch"
+    assert torch.isfinite(a).all()
