@@ -37,6 +37,7 @@ typedef struct mdb_unet_config {
   int use_pos_bias;        /* 1: stem adds pos_layer(coords*0) = its bias (ddpm_res64.py:148) */
   int max_batch;
   int precision;           /* 0 = bf16 operands, 1 = tf32 operands; fp32 accumulation either way */
+  int training;            /* 1 = also build the backward plan (bf16 operands only) and keep what it needs */
 } mdb_unet_config;
 
 int mdb_unet_create(const mdb_unet_config* cfg, mdb_unet** out);
@@ -62,6 +63,23 @@ int mdb_unet_info(mdb_unet* net, double* flops_per_sample, long long* arena_byte
 int mdb_unet_profile(mdb_unet* net, const float* x, const float* labels, float* out, int batch, void* stream,
                      char* names_buf, int names_len, float* ms, int max_steps, int* n_steps);
 
+/* ---- training (engines created with cfg.training = 1). Replaces `loss.backward()` through score_model
+ * (lib/diffusion/losses.py:104-139 -> torch autograd over ddpm_res64.py:126-199).
+ * Dropout of the next forward/backward pair (nn.Dropout(p) after GroupNorm_1+SiLU, layers.py:661,682); p = 0 is
+ * model.eval(). The same (p, seed) must be in force for a forward and its backward. */
+int mdb_unet_set_dropout(mdb_unet* net, float p, unsigned long long seed);
+/* dout = dL/d(out) of the immediately preceding mdb_unet_forward (same x, labels, batch; x and labels must still be
+ * alive). grads: ONE flat fp32 buffer of grads_numel = sum of all parameter numels, parameter i at the offset
+ * mdb_unet_grad_offset gives (table order); slots of non-trainable tensors (mask, coords, sigmas, pos_layer.weight,
+ * whose input is coords*0) are not written. accumulate != 0: grads += (micro-batching, losses.py:111-113). */
+int mdb_unet_backward(mdb_unet* net, const float* dout, float* grads, long long grads_numel, int batch, int accumulate,
+                      void* stream);
+int mdb_unet_grad_offset(mdb_unet* net, const char* name, long long* offset);
+int mdb_unet_train_info(mdb_unet* net, double* bwd_flops_per_sample, int* n_bwd_steps, long long* total_param_numel);
+/* One profiled backward (same contract as mdb_unet_profile). */
+int mdb_unet_profile_backward(mdb_unet* net, const float* dout, float* grads, int batch, void* stream, char* names_buf,
+                              int names_len, float* ms, int max_steps, int* n_steps);
+
 /* Position-weighted 64-bit fingerprints of n fp32 device tensors (ptrs_dev / numels_dev / out_dev are device
  * arrays of n entries). Host plumbing for load_state_dict-style change detection; no reference counterpart. */
 int mdb_fingerprint(const void* const* ptrs_dev, const long long* numels_dev, int n, unsigned long long* out_dev,
@@ -86,7 +104,7 @@ int mdb_sampler_run(mdb_unet* net, float* x, float* x_mean, const float* mask, c
  * Training-step kernels (optimiser side). Replace get_ddpm_loss_fn's elementwise tail (lib/diffusion/losses.py:69-78),
  * torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (losses.py:45-50, 26-35) and
  * ExponentialMovingAverage.update (lib/diffusion/models/ema.py:43-64). Pointer tables / numels are DEVICE arrays of
- * n entries (one per parameter tensor); `scratch` is one device double. The network backward is not part of round 1.
+ * n entries (one per parameter tensor); `scratch` is one device double.
  */
 /* loss = mean_b[mean_{c,v}((pred-noise)^2 mask[v])] * V / mask_sum -> *loss_out; grad_pred (nullable) = dloss/dpred. */
 int mdb_ddpm_loss(const float* pred, const float* noise, const float* mask, double mask_sum, float* loss_out,
@@ -115,6 +133,18 @@ int mdb_conv3d(const void* x, int batch, int cin, int z, int y_, int x_, const f
  * y [B][V][C]. */
 int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma, const float* beta, void* y, int batch,
                       long long voxels, int channels, int silu, int precision, void* stream);
+
+/* Backward of mdb_conv3d for bf16 operands (k = 3 stride 1 | 2, or k = 1): what autograd's conv3d backward returns.
+ * dy: [B][Zo][Yo][Xo][Cout], x: [B][Z][Y][X][Cin] (both bf16 NDHWC), w: fp32 OIDHW. dw (nullable): fp32 OIDHW;
+ * dx (nullable, stride 1 only): bf16 [B][Z][Y][X][Cin]. Synchronises. */
+int mdb_conv3d_backward(const void* dy, const void* x, const float* w, int batch, int cin, int cout, int z, int y_,
+                        int x_, int ksize, int stride, float* dw, void* dx, void* stream);
+/* Backward of mdb_groupnorm_act (bf16): da = dL/dy [B][V][C] -> dx [B][V][C], dgamma / dbeta fp32 [C]. `add`
+ * (nullable, [B][V][C]) is summed into dx. Dropout (p, seed) as in mdb_unet_set_dropout. Synchronises. */
+int mdb_groupnorm_act_backward(const void* x, const long long* stats, const float* gamma, const float* beta,
+                               const void* da, const void* add, void* dx, float* dgamma, float* dbeta, int batch,
+                               long long voxels, int channels, int silu, float dropout_p, unsigned long long seed,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Marching tetrahedra. Replaces DMTet.__call__ (nvdiffrec/lib/geometry/dmtet.py:105-163; tables :34-54, map_uv

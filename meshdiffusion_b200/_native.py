@@ -30,6 +30,7 @@ class UNetConfigC(ctypes.Structure):
         ("use_pos_bias", ctypes.c_int),
         ("max_batch", ctypes.c_int),
         ("precision", ctypes.c_int),
+        ("training", ctypes.c_int),
     ]
 
 
@@ -49,6 +50,11 @@ SIGNATURES = {
     "mdb_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "mdb_unet_info": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_ll), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "mdb_unet_profile": (_i, [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_char_p, _i, ctypes.POINTER(_f), _i, ctypes.POINTER(_i)]),
+    "mdb_unet_set_dropout": (_i, [_vp, _f, _u64]),
+    "mdb_unet_backward": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "mdb_unet_grad_offset": (_i, [_vp, ctypes.c_char_p, ctypes.POINTER(_ll)]),
+    "mdb_unet_train_info": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_i), ctypes.POINTER(_ll)]),
+    "mdb_unet_profile_backward": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.c_char_p, _i, ctypes.POINTER(_f), _i, ctypes.POINTER(_i)]),
     "mdb_fingerprint": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mdb_sampler_update": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _u64, _u64, _vp]),
     "mdb_sampler_run": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_f), _i, _i, _u64, _vp, _vp, _vp]),
@@ -57,6 +63,8 @@ SIGNATURES = {
     "mdb_adam_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "mdb_conv3d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "mdb_groupnorm_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp]),
+    "mdb_conv3d_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mdb_groupnorm_act_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _u64, _vp]),
     "mdb_marching_tets_prepare": (_i, [_vp, _i, _i, _i, ctypes.POINTER(_vp)]),
     "mdb_marching_tets_destroy": (None, [_vp]),
     "mdb_marching_tets_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),

@@ -2,6 +2,7 @@
 #include "../../include/meshdiff_b200.h"
 #include "unet.h"
 #include <cstring>
+#include <cmath>
 
 using namespace mdb;
 
@@ -38,7 +39,7 @@ static int create_impl(const mdb_unet_config* c, mdb_unet** out, bool dry) {
   u.n_attn = c->n_attn;
   for (int i = 0; i < 4; ++i) u.attn_resolutions[i] = c->attn_resolutions[i];
   u.num_channels = c->num_channels; u.stem_ksize = c->stem_ksize; u.use_pos_bias = c->use_pos_bias;
-  u.max_batch = c->max_batch; u.precision = c->precision;
+  u.max_batch = c->max_batch; u.precision = c->precision; u.training = c->training;
   auto* h = new mdb_unet;
   h->net = nullptr;
   try { h->net = new UNet(u, dry); } catch (...) { delete h; throw; }
@@ -105,6 +106,50 @@ int mdb_unet_profile(mdb_unet* n, const float* x, const float* labels, float* ou
                      int names_len, float* ms, int max_steps, int* nsteps) {
   MDB_API_BEGIN
   auto r = n->net->profile(x, labels, out, B, (cudaStream_t)stream);
+  std::string all;
+  int k = 0;
+  for (auto& p : r) {
+    if (k >= max_steps) break;
+    all += p.first; all += "\n";
+    ms[k++] = p.second;
+  }
+  if ((int)all.size() + 1 > names_len) throw std::runtime_error("mdb: names buffer too small");
+  std::memcpy(names, all.c_str(), all.size() + 1);
+  if (nsteps) *nsteps = k;
+  MDB_API_END
+}
+
+int mdb_unet_set_dropout(mdb_unet* n, float p, unsigned long long seed) {
+  MDB_API_BEGIN
+  n->net->set_dropout(p, seed);
+  MDB_API_END
+}
+
+int mdb_unet_backward(mdb_unet* n, const float* dout, float* grads, long long grads_numel, int B, int accumulate, void* stream) {
+  MDB_API_BEGIN
+  if (grads_numel != n->net->total_param_numel()) throw std::runtime_error("mdb: gradient buffer has the wrong size");
+  n->net->backward(dout, grads, B, accumulate != 0, (cudaStream_t)stream);
+  MDB_API_END
+}
+
+int mdb_unet_grad_offset(mdb_unet* n, const char* name, long long* off) {
+  MDB_API_BEGIN
+  *off = n->net->grad_offset(name);
+  MDB_API_END
+}
+
+int mdb_unet_train_info(mdb_unet* n, double* bwd_flops, int* nsteps, long long* numel) {
+  MDB_API_BEGIN
+  if (bwd_flops) *bwd_flops = n->net->bwd_flops_per_sample();
+  if (nsteps) *nsteps = n->net->num_bwd_steps();
+  if (numel) *numel = n->net->total_param_numel();
+  MDB_API_END
+}
+
+int mdb_unet_profile_backward(mdb_unet* n, const float* dout, float* grads, int B, void* stream, char* names, int names_len,
+                              float* ms, int max_steps, int* nsteps) {
+  MDB_API_BEGIN
+  auto r = n->net->profile_backward(dout, grads, B, (cudaStream_t)stream);
   std::string all;
   int k = 0;
   for (auto& p : r) {
@@ -207,6 +252,59 @@ int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma,
   na.stats0 = stats; na.stats1 = nullptr; na.gamma = gamma; na.beta = beta; na.groups = 32; na.eps = 1e-6f;
   launch_norm_act(na, B, s);
   MDB_CUDA_CHECK(cudaStreamSynchronize(s));
+  MDB_API_END
+}
+
+int mdb_conv3d_backward(const void* dy, const void* x, const float* w, int B, int cin, int cout, int z, int y_, int x_,
+                        int ksize, int stride, float* dw, void* dx, void* stream) {
+  MDB_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  const int xo = x_ / stride, yo = y_ / stride, zo = z / stride;
+  Act ady; ady.ptr = const_cast<void*>(dy); ady.C = cout; ady.X = xo; ady.Y = yo; ady.Z = zo; ady.B = B;
+  Act ax; ax.ptr = const_cast<void*>(x); ax.C = cin; ax.X = x_; ax.Y = y_; ax.Z = z; ax.B = B;
+  if (dw) {
+    const int T = ksize * ksize * ksize;
+    const WgradPlan pl = plan_wgrad(xo, yo, zo, B, cout, cin, ksize, stride);
+    float* scratch = nullptr;
+    MDB_CUDA_CHECK(cudaMalloc(&scratch, pl.scratch_bytes));
+    WgradOut o; o.ptr = dw; o.sm = (long long)cin * T; o.sn = T; o.st = 1;
+    WgradOp op;
+    op.init(ady, ax, ksize, stride, o, scratch);
+    op.launch(s, B, false);
+    MDB_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(scratch);
+  }
+  if (dx) {
+    if (stride != 1) throw std::runtime_error("mdb: conv3d data gradient entry point supports stride 1");
+    GemmOp g;
+    g.set_output(kBF16, x_, y_, z, B, cin, dx, cin, false);
+    if (ksize == 1) { WSrc ws{w, 1, (long long)cin, 0, cout}; g.add_pointwise_w({ady}, &ws); }
+    else g.add_conv_dgrad(ady, w, cin, ksize);
+    g.finalize(s, true);
+    g.launch(s);
+    MDB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  MDB_API_END
+}
+
+int mdb_groupnorm_act_backward(const void* x, const long long* stats, const float* gamma, const float* beta, const void* da,
+                               const void* add, void* dx, float* dgamma, float* dbeta, int B, long long V, int C, int silu,
+                               float dropout_p, unsigned long long seed, void* stream) {
+  MDB_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  float *part = nullptr, *sums = nullptr;
+  MDB_CUDA_CHECK(cudaMalloc(&part, (size_t)kBwdMaxBlocksX * B * C * 2 * sizeof(float)));
+  MDB_CUDA_CHECK(cudaMalloc(&sums, (size_t)B * C * 2 * sizeof(float)));
+  GnBwdArgs a{};
+  a.x0 = x; a.C0 = C; a.ld0 = C; a.stats0 = stats; a.gamma = gamma; a.beta = beta; a.da = da;
+  a.voxels = V; a.silu = silu; a.groups = 32; a.eps = 1e-6f;
+  a.drop_thresh = (int)lround((double)dropout_p * 65536.0); a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f; a.seed = seed;
+  a.part = part; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta; a.accumulate = 0;
+  a.dx = dx; a.add0 = add; a.add0_ld = C;
+  launch_gn_bwd_reduce(a, B, s);
+  launch_gn_bwd_apply(a, B, s);
+  MDB_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(part); cudaFree(sums);
   MDB_API_END
 }
 

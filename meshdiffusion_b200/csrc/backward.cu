@@ -1,0 +1,519 @@
+// Bandwidth-bound kernels of the training backward pass (bf16 activations, fp32 parameter gradients).
+#include "backward.cuh"
+#include <stdexcept>
+#include <string>
+
+namespace mdb {
+
+#define MDB_LAUNCH_CHECK()                                                                              \
+  do {                                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                                \
+    if (_e != cudaSuccess) throw std::runtime_error(std::string("mdb launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int VEC = 8;  // bf16 elements per 16-byte vector
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float* x) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+  return t;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float dsilu(float y) {
+  const float s = sigmoid_fast(y);
+  return s * fmaf(y, 1.f - s, 1.f);
+}
+
+// grid.x for the staged reductions: enough blocks to fill the machine, at most kBwdMaxBlocksX per sample
+static inline int blocks_x(long long voxels, int k, int B) {
+  long long gx = (voxels + (long long)k * 4 - 1) / ((long long)k * 4);
+  long long want = (148LL * 8 + B - 1) / B;
+  if (want > kBwdMaxBlocksX) want = kBwdMaxBlocksX;
+  if (gx > want) gx = want;
+  return gx < 1 ? 1 : (int)gx;
+}
+
+// mean / rstd of the GroupNorm group of each of the thread's VEC channels, from the forward statistics
+__device__ __forceinline__ void gn_stats_of(const GnBwdArgs& a, int b, int c, float* mean, float* rstd) {
+  const int C = a.C0 + a.C1;
+  const int cpg = C / a.groups;
+  const double n = (double)a.voxels * cpg;
+  int cur_g = -1;
+  float m = 0.f, r = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int g = (c + j) / cpg;
+    if (g != cur_g) {
+      cur_g = g;
+      long long s1 = 0, s2 = 0;
+      for (int i = 0; i < cpg; ++i) {
+        const int cc = g * cpg + i;
+        const long long* q = (cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * 2 : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * 2;
+        s1 += q[0]; s2 += q[1];
+      }
+      const double mm = (double)s1 * (1.0 / 16777216.0) / n;
+      double var = (double)s2 * (1.0 / 16777216.0) / n - mm * mm;
+      if (var < 0) var = 0;
+      m = (float)mm;
+      r = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
+    mean[j] = m; rstd[j] = r;
+  }
+}
+
+// dy[j] = da[j] * act'(y[j]) * dropout, xh[j] = normalised input
+__device__ __forceinline__ void gn_dy(const GnBwdArgs& a, const float* x, const float* da, const float* mean, const float* rstd,
+                                      const float* g, const float* be, long long e0, float* xh, float* dy) {
+  unsigned long long h0 = 0, h1 = 0;
+  if (a.drop_thresh > 0) { h0 = drop_hash64(a.seed, (unsigned long long)(e0 >> 2)); h1 = drop_hash64(a.seed, (unsigned long long)(e0 >> 2) + 1); }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    xh[j] = (x[j] - mean[j]) * rstd[j];
+    float d = da[j];
+    if (a.drop_thresh > 0) {
+      const unsigned r16 = (unsigned)(((j < 4 ? h0 : h1) >> (16 * (j & 3))) & 0xFFFFu);
+      d = r16 >= (unsigned)a.drop_thresh ? d * a.drop_scale : 0.f;
+    }
+    if (a.silu) d *= dsilu(fmaf(g[j], xh[j], be[j]));
+    dy[j] = d;
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs a, int cv, int k) {
+  __shared__ float red[256 * VEC * 2];
+  const int C = a.C0 + a.C1;
+  const int b = blockIdx.y;
+  const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
+  const int c = cvi * VEC;
+  float mean[VEC], rstd[VEC], g[VEC], be[VEC];
+  gn_stats_of(a, b, c, mean, rstd);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { g[j] = a.gamma[c + j]; be[j] = a.beta[c + j]; }
+  const bool first = c < a.C0;
+  const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 + c) * 2
+                          : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 + (c - a.C0)) * 2;
+  const long long src_stride = (first ? a.ld0 : a.ld1) * 2;
+  const char* dsrc = (const char*)a.da + ((long long)b * a.voxels * C + c) * 2;
+  const long long d_stride = (long long)C * 2;
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const long long step = (long long)gridDim.x * k;
+  for (long long v = (long long)blockIdx.x * k + vl; v < a.voxels; v += step) {
+    const uint4 rx = __ldg((const uint4*)(src + v * src_stride));
+    const uint4 rd = __ldg((const uint4*)(dsrc + v * d_stride));
+    float x[VEC], da[VEC], xh[VEC], dy[VEC];
+    unpack8(rx, x); unpack8(rd, da);
+    gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], xh[j], s2[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { red[(threadIdx.x * VEC + j) * 2] = s1[j]; red[(threadIdx.x * VEC + j) * 2 + 1] = s2[j]; }
+  __syncthreads();
+  if (vl == 0) {
+    for (int j = 0; j < VEC; ++j) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int l = 0; l < k; ++l) { t1 += red[((l * cv + cvi) * VEC + j) * 2]; t2 += red[((l * cv + cvi) * VEC + j) * 2 + 1]; }
+      float* o = a.part + (((long long)blockIdx.x * gridDim.y + b) * C + c + j) * 2;
+      o[0] = t1; o[1] = t2;
+    }
+  }
+}
+
+__global__ void gn_bwd_sums_kernel(const float* __restrict__ part, float* __restrict__ sums, int gx, int BC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC) return;
+  float t1 = 0.f, t2 = 0.f;
+  for (int x = 0; x < gx; ++x) { t1 += part[((long long)x * BC + i) * 2]; t2 += part[((long long)x * BC + i) * 2 + 1]; }
+  sums[2 * i] = t1; sums[2 * i + 1] = t2;
+}
+__global__ void gn_bwd_param_kernel(const float* __restrict__ sums, float* dgamma, float* dbeta, int B, int C, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t1 = 0.f, t2 = 0.f;
+  for (int b = 0; b < B; ++b) { t1 += sums[((long long)b * C + c) * 2]; t2 += sums[((long long)b * C + c) * 2 + 1]; }
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + t1;
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + t2;
+}
+
+static void gn_launch_shape(const GnBwdArgs& a, int& cv, int& k) {
+  const int C = a.C0 + a.C1;
+  cv = C / VEC;
+  if (cv < 1 || cv > 256 || C % VEC != 0 || a.C0 % VEC != 0) throw std::runtime_error("mdb: unsupported channel count in GroupNorm backward");
+  k = 256 / cv;
+}
+
+void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s) {
+  int cv, k;
+  gn_launch_shape(a, cv, k);
+  const int C = a.C0 + a.C1;
+  const int gx = blocks_x(a.voxels, k, B);
+  gn_bwd_reduce_kernel<<<dim3(gx, B), cv * k, 0, s>>>(a, cv, k);
+  MDB_LAUNCH_CHECK();
+  gn_bwd_sums_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a.part, a.sums, gx, B * C);
+  MDB_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(a.sums, a.dgamma, a.dbeta, B, C, a.accumulate);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
+  const int C = a.C0 + a.C1;
+  const int b = blockIdx.y;
+  const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
+  const int c = cvi * VEC;
+  float mean[VEC], rstd[VEC], g[VEC], be[VEC], c1[VEC], m1[VEC], m2[VEC];
+  gn_stats_of(a, b, c, mean, rstd);
+  {
+    const int cpg = C / a.groups;
+    const float inv_n = 1.f / ((float)a.voxels * (float)cpg);
+    int cur_g = -1;
+    float A = 0.f, Bq = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      g[j] = a.gamma[c + j]; be[j] = a.beta[c + j];
+      const int gidx = (c + j) / cpg;
+      if (gidx != cur_g) {
+        cur_g = gidx;
+        A = 0.f; Bq = 0.f;
+        for (int i = 0; i < cpg; ++i) {
+          const int cc = gidx * cpg + i;
+          const float gm = a.gamma[cc];
+          A = fmaf(gm, a.sums[((long long)b * C + cc) * 2], A);
+          Bq = fmaf(gm, a.sums[((long long)b * C + cc) * 2 + 1], Bq);
+        }
+      }
+      c1[j] = rstd[j] * g[j];
+      m1[j] = rstd[j] * A * inv_n;
+      m2[j] = rstd[j] * Bq * inv_n;
+    }
+  }
+  const bool first = c < a.C0;
+  const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 + c) * 2
+                          : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 + (c - a.C0)) * 2;
+  const long long src_stride = (first ? a.ld0 : a.ld1) * 2;
+  const char* dsrc = (const char*)a.da + ((long long)b * a.voxels * C + c) * 2;
+  const long long d_stride = (long long)C * 2;
+  char* dst = (char*)a.dx + ((long long)b * a.voxels * C + c) * 2;
+  const char* p0 = a.add0 ? (const char*)a.add0 + ((long long)b * a.voxels * a.add0_ld + c) * 2 : nullptr;
+  const char* p1 = a.add1 ? (const char*)a.add1 + ((long long)b * a.voxels * a.add1_ld + c) * 2 : nullptr;
+  const long long step = (long long)gridDim.x * k;
+  for (long long v = (long long)blockIdx.x * k + vl; v < a.voxels; v += step) {
+    const uint4 rx = __ldg((const uint4*)(src + v * src_stride));
+    const uint4 rd = __ldg((const uint4*)(dsrc + v * d_stride));
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+    if (p0) r0 = __ldg((const uint4*)(p0 + v * a.add0_ld * 2));
+    if (p1) r1 = __ldg((const uint4*)(p1 + v * a.add1_ld * 2));
+    float x[VEC], da[VEC], xh[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
+    unpack8(rx, x); unpack8(rd, da); unpack8(r0, e0); unpack8(r1, e1);
+    gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = fmaf(c1[j], dy[j], -m1[j]) - xh[j] * m2[j] + e0[j] + e1[j];
+    *((uint4*)(dst + v * d_stride)) = pack8(o);
+  }
+}
+
+void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s) {
+  int cv, k;
+  gn_launch_shape(a, cv, k);
+  long long gx = (a.voxels + (long long)k * 4 - 1) / ((long long)k * 4);
+  const long long cap = (148LL * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  gn_bwd_apply_kernel<<<dim3((unsigned)gx, B), cv * k, 0, s>>>(a, cv, k);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ column sums (bias / time-embedding gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a, int cv, int k) {
+  __shared__ float red[256 * VEC];
+  const int b = blockIdx.y;
+  const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
+  const int c = cvi * VEC;
+  const char* src = (const char*)a.t + ((long long)b * a.voxels * a.ld + c) * 2;
+  float s1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s1[j] = 0.f;
+  const long long step = (long long)gridDim.x * k;
+  for (long long v = (long long)blockIdx.x * k + vl; v < a.voxels; v += step) {
+    float x[VEC];
+    unpack8(__ldg((const uint4*)(src + v * a.ld * 2)), x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s1[j] += x[j];
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = s1[j];
+  __syncthreads();
+  if (vl == 0) {
+    for (int j = 0; j < VEC; ++j) {
+      float t = 0.f;
+      for (int l = 0; l < k; ++l) t += red[(l * cv + cvi) * VEC + j];
+      a.part[((long long)blockIdx.x * gridDim.y + b) * a.C + c + j] = t;
+    }
+  }
+}
+__global__ void colsum_final_kernel(ColsumArgs a, int gx, int B) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  float tot = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float t = 0.f;
+    for (int x = 0; x < gx; ++x) t += a.part[((long long)x * B + b) * a.C + c];
+    if (a.per) a.per[(long long)b * a.per_ld + c] = t;
+    tot += t;
+  }
+  if (a.total0) a.total0[c] = (a.accumulate ? a.total0[c] : 0.f) + tot;
+  if (a.total1) a.total1[c] = (a.accumulate ? a.total1[c] : 0.f) + tot;
+  if (a.total2) a.total2[c] = (a.accumulate ? a.total2[c] : 0.f) + tot;
+}
+void launch_colsum(const ColsumArgs& a, int B, cudaStream_t s) {
+  const int cv = a.C / VEC;
+  if (cv < 1 || cv > 256 || a.C % VEC != 0) throw std::runtime_error("mdb: unsupported channel count in colsum");
+  const int k = 256 / cv;
+  const int gx = blocks_x(a.voxels, k, B);
+  colsum_kernel<<<dim3(gx, B), cv * k, 0, s>>>(a, cv, k);
+  MDB_LAUNCH_CHECK();
+  colsum_final_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a, gx, B);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ resampling data movement
+static inline int grid_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = 148LL * 8;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : (int)b;
+}
+
+__global__ void zero_stuff2x_kernel(const uint4* __restrict__ dy, uint4* __restrict__ z, int B, int R, int cv) {
+  const int R2 = 2 * R;
+  const long long total = (long long)B * R2 * R2 * R2 * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int c = (int)(r % cv); r /= cv;
+    const int xo = (int)(r % R2); r /= R2;
+    const int yo = (int)(r % R2); r /= R2;
+    const int zo = (int)(r % R2); r /= R2;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((xo & yo & zo & 1) != 0) v = __ldg(dy + ((((long long)r * R + (zo >> 1)) * R + (yo >> 1)) * R + (xo >> 1)) * cv + c);
+    z[i] = v;
+  }
+}
+void launch_zero_stuff2x(const void* dy, void* z, int B, int R, int C, cudaStream_t s) {
+  const int cv = C / VEC;
+  const long long total = (long long)B * 8 * R * R * R * cv;
+  zero_stuff2x_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint4*)dy, (uint4*)z, B, R, cv);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void downsum2x_kernel(const uint4* __restrict__ dup, uint4* __restrict__ dx, int B, int R, int cv) {
+  const int R2 = 2 * R;
+  const long long total = (long long)B * R * R * R * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int c = (int)(r % cv); r /= cv;
+    const int xo = (int)(r % R); r /= R;
+    const int yo = (int)(r % R); r /= R;
+    const int zo = (int)(r % R); r /= R;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int dz = 0; dz < 2; ++dz)
+      for (int dyy = 0; dyy < 2; ++dyy)
+        for (int dxx = 0; dxx < 2; ++dxx) {
+          float t[VEC];
+          unpack8(__ldg(dup + ((((long long)r * R2 + 2 * zo + dz) * R2 + 2 * yo + dyy) * R2 + 2 * xo + dxx) * cv + c), t);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] += t[j];
+        }
+    dx[i] = pack8(acc);
+  }
+}
+void launch_downsum2x(const void* dup, void* dx, int B, int R, int C, cudaStream_t s) {
+  const int cv = C / VEC;
+  const long long total = (long long)B * R * R * R * cv;
+  downsum2x_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint4*)dup, (uint4*)dx, B, R, cv);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void batch_sum_kernel(const uint4* __restrict__ t, uint4* __restrict__ out, int B, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float x[VEC];
+      unpack8(__ldg(t + (long long)b * n + i), x);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] += x[j];
+    }
+    out[i] = pack8(acc);
+  }
+}
+void launch_batch_sum(const void* t, void* out, int B, long long VC, cudaStream_t s) {
+  const long long n = VC / VEC;
+  batch_sum_kernel<<<grid_for(n, 256), 256, 0, s>>>((const uint4*)t, (uint4*)out, B, n);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(1024) rowsum_nc_kernel(const float* __restrict__ t, float* out, int B, int C, long long V, int accumulate) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* p = t + ((long long)b * C + c) * V;
+    for (long long v = threadIdx.x; v < V; v += blockDim.x) acc += __ldg(p + v);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    out[c] = (accumulate ? out[c] : 0.f) + tot;
+  }
+}
+void launch_rowsum_nc(const float* t, float* out, int B, int C, long long V, int accumulate, cudaStream_t s) {
+  rowsum_nc_kernel<<<C, 1024, 0, s>>>(t, out, B, C, V, accumulate);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ attention softmax backward (layers.py:604)
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const float* __restrict__ P, float* __restrict__ dP, long long rows, int L) {
+  __shared__ float red[8];
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(P + row * L);
+    float* d = dP + row * L;
+    float pv[16], dv[16];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = threadIdx.x + j * 256;
+      pv[j] = i < L ? __bfloat162float(p[i]) : 0.f;
+      dv[j] = i < L ? d[i] : 0.f;
+      dot = fmaf(pv[j], dv[j], dot);
+    }
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();  // also: every thread has read its dP values before anyone overwrites the row
+    dot = 0.f;
+    for (int w = 0; w < 8; ++w) dot += red[w];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = threadIdx.x + j * 256;
+      if (i < L) reinterpret_cast<__nv_bfloat16*>(d)[i] = __float2bfloat16(pv[j] * (dv[j] - dot));
+    }
+  }
+}
+void launch_softmax_bwd_rows(const float* P, float* dP, long long rows, int L, cudaStream_t s) {
+  if (L > 16 * 256) throw std::runtime_error("mdb: softmax row too long");
+  const int grid = (int)(rows < 148LL * 16 ? rows : 148LL * 16);
+  softmax_bwd_rows_kernel<<<grid, 256, 0, s>>>(P, dP, rows, L);
+  MDB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------ small fp32 linear-layer gradients (time embedding)
+__global__ void outer_sum_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ x, long long x_ld,
+                                 float* dW, float* db, int B, int N, int K, int accumulate) {
+  const long long total = (long long)N * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(dy[b * dy_ld + n], x[b * x_ld + k], acc);
+    dW[i] = (accumulate ? dW[i] : 0.f) + acc;
+    if (k == 0 && db) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t += dy[b * dy_ld + n];
+      db[n] = (accumulate ? db[n] : 0.f) + t;
+    }
+  }
+}
+void launch_outer_sum(const float* dy, long long dy_ld, const float* x, long long x_ld, float* dW, float* db, int B, int N, int K,
+                      int accumulate, cudaStream_t s) {
+  outer_sum_kernel<<<grid_for((long long)N * K, 256), 256, 0, s>>>(dy, dy_ld, x, x_ld, dW, db, B, N, K, accumulate);
+  MDB_LAUNCH_CHECK();
+}
+
+__global__ void dense_bwd_input_kernel(const float* __restrict__ dy, long long dy_ld, const float* __restrict__ W, float* __restrict__ dx,
+                                       int B, int N, int K) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc = fmaf(dy[b * dy_ld + n], __ldg(W + (long long)n * K + k), acc);
+  dx[(long long)b * K + k] = acc;
+}
+void launch_dense_bwd_input(const float* dy, long long dy_ld, const float* W, float* dx, int B, int N, int K, cudaStream_t s) {
+  dense_bwd_input_kernel<<<dim3((K + 127) / 128, B), 128, 0, s>>>(dy, dy_ld, W, dx, B, N, K);
+  MDB_LAUNCH_CHECK();
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// One block per sample. Recomputes emb -> t1 -> h1 -> t2 (elementwise.cu temb_kernel), then
+// dt2 = dact * silu'(t2), dh1 = W1^T dt2, dt1 = dh1 * silu'(t1).
+__global__ void temb_bwd_kernel(const float* __restrict__ labels, const float* __restrict__ w0, const float* __restrict__ b0,
+                                const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ dact,
+                                float* __restrict__ dt2, float* __restrict__ h1o, float* __restrict__ dt1, float* __restrict__ embo, int nf) {
+  extern __shared__ float sm[];
+  const int H = 4 * nf;
+  float* emb = sm;          // nf
+  float* t1 = sm + nf;      // H
+  float* h1 = t1 + H;       // H
+  float* d2 = h1 + H;       // H
+  const int b = blockIdx.x;
+  const int half = nf / 2;
+  const float t = labels[b];
+  for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+    const int k = i < half ? i : i - half;
+    const float coef = logf(10000.f) / (float)(half - 1);
+    const float f = expf((float)k * -coef);
+    const float arg = t * f;
+    emb[i] = i < half ? sinf(arg) : cosf(arg);
+    embo[(long long)b * nf + i] = emb[i];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < H; n += blockDim.x) {
+    float acc = b0[n];
+    for (int k = 0; k < nf; ++k) acc += w0[(long long)n * nf + k] * emb[k];
+    t1[n] = acc;
+    const float sg = sigmoid_f(acc);
+    h1[n] = acc * sg;
+    h1o[(long long)b * H + n] = h1[n];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < H; n += blockDim.x) {
+    float acc = b1[n];
+    for (int k = 0; k < H; ++k) acc += w1[(long long)n * H + k] * h1[k];
+    const float sg = sigmoid_f(acc);
+    const float d = dact[(long long)b * H + n] * sg * (1.f + acc * (1.f - sg));
+    d2[n] = d;
+    dt2[(long long)b * H + n] = d;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float acc = 0.f;
+    for (int n = 0; n < H; ++n) acc = fmaf(d2[n], __ldg(w1 + (long long)n * H + k), acc);
+    const float sg = sigmoid_f(t1[k]);
+    dt1[(long long)b * H + k] = acc * sg * (1.f + t1[k] * (1.f - sg));
+  }
+}
+void launch_temb_bwd(const float* labels, const float* w0, const float* b0, const float* w1, const float* b1, const float* dact,
+                     float* dt2, float* h1, float* dt1, float* emb, int B, int nf, cudaStream_t s) {
+  temb_bwd_kernel<<<B, 256, (nf + 12 * nf) * sizeof(float), s>>>(labels, w0, b0, w1, b1, dact, dt2, h1, dt1, emb, nf);
+  MDB_LAUNCH_CHECK();
+}
+
+}  // namespace mdb

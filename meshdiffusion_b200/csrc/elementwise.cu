@@ -1,4 +1,5 @@
 #include "elementwise.cuh"
+#include "backward.cuh"
 #include <curand_kernel.h>
 #include <stdexcept>
 #include <string>
@@ -151,6 +152,15 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, in
         float y = fmaf(x[j], sc[j], sh[j]);
         if (a.silu) y = TF32 ? silu_f(y) : silu_fast(y);
         x[j] = y;
+      }
+      if (!TF32 && a.drop_thresh > 0) {
+        const unsigned long long e4 = (unsigned long long)((((long long)b * a.voxels + v) * C + c) >> 2);
+        const unsigned long long h0 = drop_hash64(a.seed, e4), h1 = drop_hash64(a.seed, e4 + 1);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const unsigned r16 = (unsigned)(((j < 4 ? h0 : h1) >> (16 * (j & 3))) & 0xFFFFu);
+          x[j] = r16 >= (unsigned)a.drop_thresh ? x[j] * a.drop_scale : 0.f;
+        }
       }
       if (TF32) {
         *((float4*)(dst + v * dst_stride)) =

@@ -28,6 +28,8 @@ struct NormActArgs {
   const long long* stats0; const long long* stats1;
   const float* gamma; const float* beta;
   int groups; float eps;
+  // training: nn.Dropout after the activation (layers.py:661,682): keep iff hash16(seed, element) >= drop_thresh
+  int drop_thresh; float drop_scale; unsigned long long seed;
 };
 void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s);
 

@@ -26,8 +26,8 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static void encode_map(CUtensorMap* m, Precision prec, int rank, void* base, const uint64_t* dims,
-                       const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+void encode_map(CUtensorMap* m, Precision prec, int rank, void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bd[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = 1; }
@@ -182,11 +182,25 @@ void GemmOp::add_load(int tmap, int nk, int rows, int jrows, int dx, int dy, int
 }
 
 void GemmOp::add_conv(const std::vector<Act>& srcs, const float* w, int k, int stride) {
+  int ctot = 0;
+  for (auto& s : srcs) ctot += s.C;
+  const int T = k * k * k;
+  add_conv_w(srcs, WSrc{w, 1LL * ctot * T, (long long)T, 1, ctot}, k, stride);
+}
+
+// Data gradient of a stride-1 k^3 convolution = the same convolution over dY with the weight transposed (Cout <-> Cin)
+// and every tap mirrored: W'[ci][co][tap] = W[co][ci][T-1-tap].
+void GemmOp::add_conv_dgrad(const Act& dy, const float* w_oidhw, int cin_total, int k) {
+  const int T = k * k * k;
+  add_conv_w({dy}, WSrc{w_oidhw + (T - 1), (long long)T, 1LL * cin_total * T, -1, dy.C}, k, 1);
+}
+
+void GemmOp::add_conv_w(const std::vector<Act>& srcs, const WSrc& wsrc, int k, int stride) {
   const int KB = kb_elems(prec);
   int ctot = 0;
   for (auto& s : srcs) ctot += s.C;
   const int T = k * k * k;
-  const int ws = add_wsrc({w, 1LL * ctot * T, (long long)T, 1, ctot});
+  const int ws = add_wsrc(wsrc);
   const int pad = k / 2;
   flops += 2.0 * p.X * p.Y * p.Z * p.Bn * (double)p.N * ctot * T;
   int coff = 0;
@@ -275,7 +289,7 @@ void GemmOp::set_b_activation(void* ptr, int K, int N, int batch, long long rs, 
 }
 
 // ------------------------------------------------------------------ weight packing (device gather)
-struct PackWSrc { const float* ptr; long long sn, sc, st; int cvalid; int ndiv; long long sn_hi; };
+struct PackWSrc { const float* ptr; long long sn, sc, st; int cvalid; int ndiv; long long sn_hi; int cdiv; long long sc_hi; };
 struct PackArgs { PackWSrc w[4]; };
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -304,7 +318,8 @@ __global__ void pack_weights_kernel(const LoadEntry* __restrict__ loads, const i
     float v = 0.f;
     if (c < w.cvalid) {
       const long long noff = w.ndiv ? (long long)(n % w.ndiv) * w.sn + (long long)(n / w.ndiv) * w.sn_hi : (long long)n * w.sn;
-      v = w.ptr[noff + c * w.sc + tap * w.st];
+      const long long coff = w.cdiv ? (long long)(c % w.cdiv) * w.sc + (long long)(c / w.cdiv) * w.sc_hi : (long long)c * w.sc;
+      v = w.ptr[noff + coff + tap * w.st];
     }
     if (TF32) reinterpret_cast<float*>(out)[idx] = round_tf32(v);
     else reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16(v);
@@ -325,7 +340,7 @@ void GemmOp::repack(cudaStream_t stream) {
   MDB_CUDA_CHECK(cudaMemcpyAsync(d_b, ks0.data(), ks0.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   if (wsrcs.size() > 4) throw std::runtime_error("mdb: too many weight sources");
   PackArgs args{};
-  for (size_t i = 0; i < wsrcs.size(); ++i) args.w[i] = {wsrcs[i].ptr, wsrcs[i].sn, wsrcs[i].sc, wsrcs[i].st, wsrcs[i].cvalid, wsrcs[i].ndiv, wsrcs[i].sn_hi};
+  for (size_t i = 0; i < wsrcs.size(); ++i) args.w[i] = {wsrcs[i].ptr, wsrcs[i].sn, wsrcs[i].sc, wsrcs[i].st, wsrcs[i].cvalid, wsrcs[i].ndiv, wsrcs[i].sn_hi, wsrcs[i].cdiv, wsrcs[i].sc_hi};
   const long long total = 1LL * ksteps * kb_elems(prec) * p.N;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

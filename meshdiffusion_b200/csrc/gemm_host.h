@@ -40,6 +40,9 @@ struct WSrc {
   // optional split of the output index: n -> (n / ndiv, n % ndiv) addressed with strides (sn_hi, sn)
   int ndiv = 0;
   long long sn_hi = 0;
+  // optional split of the channel index: c -> (c / cdiv, c % cdiv) addressed with strides (sc_hi, sc)
+  int cdiv = 0;
+  long long sc_hi = 0;
 };
 
 struct Geometry { int bx, by, bz, bb; };
@@ -81,6 +84,9 @@ class GemmOp {
   // Dense k^3 convolution (cross-correlation, zero padding k/2, stride 1 or 2 [pad-high variant]) over the channel
   // concatenation of `srcs`; weight OIDHW fp32 [N][sum C][k^3].
   void add_conv(const std::vector<Act>& srcs, const float* w_oidhw, int ksize, int stride);
+  void add_conv_w(const std::vector<Act>& srcs, const WSrc& w, int ksize, int stride);
+  // conv data gradient: N = cin_total of the forward conv, A = dY (C = forward Cout), weight fp32 OIDHW of the forward
+  void add_conv_dgrad(const Act& dy, const float* w_oidhw, int cin_total, int ksize);
   // 1x1x1 projection of the channel concatenation of `srcs` with W[in][out] (NIN layout) or [out][in] (Linear/conv).
   void add_pointwise(const std::vector<Act>& srcs, const float* w, bool w_in_out);
   // same with an explicit weight view (nullptr = no packed weights: B comes from set_b_activation)
@@ -112,6 +118,8 @@ class GemmOp {
 };
 
 int sm_count();
+void encode_map(CUtensorMap* m, Precision prec, int rank, void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box);
 // Split-K factor for a conv-like op (pure function of the shapes, so the dry planning pass and the real pass agree).
 int plan_splits(int X, int Y, int Z, int B, int N, int cin_total, int taps, Precision prec);
 

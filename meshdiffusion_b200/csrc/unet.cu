@@ -96,8 +96,12 @@ TensP UNet::new_act(int C, int R, bool stats) {
   return t;
 }
 
+// Inference: the arena block is recycled as soon as the last forward consumer has been emitted. Training: every
+// activation is an input of some backward op, so blocks stay until the owning backward emitter frees them.
 void UNet::release(TensP& t) {
+  if (train_) return;
   arena_.release(t->off);
+  t->live = false;
   t.reset();
 }
 
@@ -136,7 +140,7 @@ GemmOp* UNet::new_gemm(const std::string& name, bool commit_time) {
 
 // GroupNorm(32, eps 1e-6) + optional SiLU over the channel concatenation of `ins` (torch.cat is never materialised
 // in raw form: only this normalised copy, which is the conv's A operand, exists).
-TensP UNet::gn(const std::string& pname, const std::vector<TensP>& ins, bool silu) {
+TensP UNet::gn(const std::string& pname, const std::vector<TensP>& ins, bool silu, int drop_layer) {
   int C = 0;
   for (auto& t : ins) C += t->C;
   const int R = ins[0]->R;
@@ -151,7 +155,15 @@ TensP UNet::gn(const std::string& pname, const std::vector<TensP>& ins, bool sil
   na.tf32 = prec_ == kTF32;
   na.stats0 = ins[0]->stats; na.stats1 = ins.size() > 1 ? ins[1]->stats : nullptr;
   na.gamma = gamma; na.beta = beta; na.groups = 32; na.eps = 1e-6f;
-  add_step("norm_act:" + pname, [na](cudaStream_t s, int B) { launch_norm_act(na, B, s); });
+  if (train_ && drop_layer >= 0) {
+    add_step("norm_act:" + pname, [na, this, drop_layer](cudaStream_t s, int B) {
+      NormActArgs a = na;
+      a.drop_thresh = rt_drop_thresh_; a.drop_scale = rt_drop_scale_; a.seed = rt_seed_ + 0x632BE59BD9B4E019ull * (unsigned long long)(drop_layer + 1);
+      launch_norm_act(a, B, s);
+    });
+  } else {
+    add_step("norm_act:" + pname, [na](cudaStream_t s, int B) { launch_norm_act(na, B, s); });
+  }
   return y;
 }
 
@@ -187,7 +199,7 @@ TensP UNet::resblock(const std::vector<TensP>& ins, int out_ch, int midx) {
   }
   split_end(sp0);
   release(a);
-  TensP a2 = gn(pre + "GroupNorm_1", {h}, true);
+  TensP a2 = gn(pre + "GroupNorm_1", {h}, true, midx);
   release(h);
   float* w1 = P(pre + "Conv_1.weight", {out_ch, out_ch, 3, 3, 3});
   float* b1 = P(pre + "Conv_1.bias", {out_ch});
@@ -221,6 +233,7 @@ TensP UNet::resblock(const std::vector<TensP>& ins, int out_ch, int midx) {
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
   split_end(sp1);
+  if (train_) tape_resblock(ins, a, h, a2, out, out_ch, midx, doff);
   release(a2);
   return out;
 }
@@ -280,8 +293,8 @@ TensP UNet::attn(const TensP& x, int midx) {
     g2->finalize(0, false);
     add_step(g2->name, [g2](cudaStream_t s, int B) { g2->launch(s, B); });
   }
-  arena_.release(S->off);
-  release(vT);
+  if (!train_) arena_.release(S->off);
+  { arena_.release(vT->off); vT->live = false; }  // backward multiplies by v itself (K-major there), not by v^T
   release(qkv);
   TensP out = new_act(C, R, true);
   if (!dry_) {
@@ -294,6 +307,7 @@ TensP UNet::attn(const TensP& x, int midx) {
     g->finalize(0, false);
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
+  if (train_) tape_attn(x, hn, qkv, S, O, out, midx);
   release(O);
   return out;
 }
@@ -316,6 +330,7 @@ TensP UNet::downsample(const TensP& x, int midx) {
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
   split_end(sp);
+  if (train_) tape_downsample(x, out, midx);
   return out;
 }
 
@@ -342,6 +357,7 @@ TensP UNet::upsample(const TensP& x, int midx) {
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
   split_end(sp);
+  if (train_) tape_upsample(x, up, out, midx);
   release(up);
   return out;
 }
@@ -371,6 +387,7 @@ void UNet::build() {
       launch_dense(ta, dw, db, dout, B, tdim, dt, s);
     });
   }
+  if (train_) tape_temb();
   // --- non-trainable tensors carried by the checkpoint
   float* mask = P("mask", {1, 1, R0, R0, R0});
   if (cfg_.use_pos_bias) P("coords", {1, 3, R0, R0, R0});
@@ -391,10 +408,11 @@ void UNet::build() {
   A0->off = arena_.alloc(A0->bytes);
   A0->ptr = dry_ ? nullptr : arena_base_ + A0->off;
   TensP h0 = new_act(nf, R0, true);
+  void* Am = nullptr;
   if (!dry_) {
     // constant field (fp32 [V][nf]) computed once per commit with the same kernels
     float* field = (float*)dmalloc(V0 * nf * 4);
-    void* Am = dmalloc(V0 * Kpad_m * esize(prec_));
+    Am = dmalloc(V0 * Kpad_m * esize(prec_));
     float* fbias = (float*)dmalloc(nf * 4);
     const int tf = prec_ == kTF32;
     const bool use_pos = cfg_.use_pos_bias != 0;
@@ -423,6 +441,7 @@ void UNet::build() {
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
   arena_.release(A0->off);
+  if (train_) tape_stem(h0, Am, Kpad, Kpad_m);
 
   // --- down path
   std::vector<TensP> hs;
@@ -477,7 +496,9 @@ void UNet::build() {
   }
   if (!hs.empty()) throw std::runtime_error("mdb: skip stack not empty");
   // --- head: GroupNorm -> SiLU -> conv(nf -> channels)
+  const std::string head_gn = "all_modules." + std::to_string(m);
   TensP a = gn("all_modules." + std::to_string(m++), {h}, true);
+  TensP head_in = h;
   release(h);
   float* hw = P("all_modules." + std::to_string(m) + ".weight", {Cin, nf, k, k, k});
   float* hb = P("all_modules." + std::to_string(m) + ".bias", {Cin});
@@ -513,14 +534,23 @@ void UNet::build() {
     g->finalize(0, false);
     add_step(g->name, [g, this](cudaStream_t s, int B) { g->launch(s, B, rt_out_); });
   }
+  if (train_) tape_head(head_in, a, head_gn, "all_modules." + std::to_string(m - 1));
   release(a);
   dense_total_ = dense_cursor_;
   stats_doubles_ = stats_cursor_;
+  if (train_) {
+    // emit the backward plan: the emitters recorded during the forward pass, in reverse order
+    for (auto it = tape_.rbegin(); it != tape_.rend(); ++it) (*it)();
+    tape_.clear();
+    if (arena_.in_use() != 0) throw std::runtime_error("mdb: training plan leaked " + std::to_string(arena_.in_use()) + " arena bytes");
+  }
 }
 
 UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(cfg.precision ? kTF32 : kBF16) {
   if (cfg_.image_size % (1 << (cfg_.n_levels - 1)) != 0) throw std::runtime_error("mdb: image_size not divisible by 2^(levels-1)");
   if (cfg_.nf % 32 != 0) throw std::runtime_error("mdb: nf must be a multiple of 32 (GroupNorm(32))");
+  train_ = cfg_.training != 0;
+  if (train_ && prec_ != kBF16) throw std::runtime_error("mdb: the training plan is built for bf16 operands");
   dry_ = true;
   build();
   // allocate everything the dry run sized
@@ -533,16 +563,25 @@ UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(cfg.precisio
   dense_w_ = (float*)dmalloc((size_t)dense_total_ * tdim * 4);
   dense_b_ = (float*)dmalloc((size_t)dense_total_ * 4);
   dense_out_ = (float*)dmalloc((size_t)cfg_.max_batch * dense_total_ * 4);
+  if (train_) d_dense_out_ = (float*)dmalloc((size_t)cfg_.max_batch * dense_total_ * 4);
   for (auto& p : params_)
     if (!p.external) p.d = (float*)dmalloc(p.numel * 4);
+  {
+    long long off = 0;
+    for (auto& p : params_) { goff_[p.name] = off; off += p.numel; }
+  }
   dry_ = false;
   build();
   for (auto& g : gemms_) flops_ += g->flops;
+  for (auto& g : bwd_gemms_) bwd_flops_ += g->flops;
+  for (auto& g : wgrads_) bwd_flops_ += g->flops;
   MDB_CUDA_CHECK(cudaDeviceSynchronize());
 }
 
 UNet::~UNet() {
   gemms_.clear();
+  bwd_gemms_.clear();
+  wgrads_.clear();
   commit_gemms_.clear();
   for (void* p : owned_) cudaFree(p);
 }
@@ -568,6 +607,7 @@ void UNet::get_param(const std::string& name, float* dst, long long numel, bool 
 void UNet::commit(cudaStream_t s) {
   for (auto& st : commit_steps_) st.fn(s, 1);
   for (auto& g : gemms_) g->repack(s);
+  for (auto& g : bwd_gemms_) g->repack(s);
   MDB_CUDA_CHECK(cudaStreamSynchronize(s));
   committed_ = true;
 }

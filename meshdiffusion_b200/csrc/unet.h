@@ -8,7 +8,9 @@
 #include <string>
 #include <vector>
 #include "gemm_host.h"
+#include "wgrad_host.h"
 #include "elementwise.cuh"
+#include "backward.cuh"
 
 namespace mdb {
 
@@ -26,6 +28,7 @@ struct UNetConfig {
   int use_pos_bias = 1; // ddpm_res64.py:148 adds pos_layer(coords*0) == its bias; res128 does not
   int max_batch = 1;
   int precision = 0;    // 0 = bf16 operands, 1 = tf32 operands (fp32 accumulate in TMEM either way)
+  int training = 0;     // 1: keep the activations backward needs and build the backward plan (bf16 only)
 };
 
 struct ParamInfo {
@@ -41,6 +44,7 @@ class Arena {
   size_t alloc(size_t bytes);
   void release(size_t off);
   size_t peak() const { return peak_; }
+  size_t in_use() const { size_t n = 0; for (auto& b : blocks_) if (!b.free) n += b.size; return n; }
   void reset() { blocks_.clear(); end_ = 0; }
  private:
   struct Block { size_t off, size; bool free; };
@@ -48,11 +52,24 @@ class Arena {
   size_t end_ = 0, peak_ = 0;
 };
 
+// A gradient buffer in the arena, shared by the views handed to the tensors it is the gradient of (the two halves of
+// a channel concatenation); returned to the arena when the last view is dropped.
+struct GradBuf { size_t off = 0; int refs = 0; };
+struct GradView {
+  std::shared_ptr<GradBuf> buf;
+  void* ptr = nullptr;
+  long long ld = 0;
+  int C = 0;
+  bool valid() const { return buf != nullptr; }
+};
+
 struct Tens {
   size_t off = 0, bytes = 0;
   int C = 0, R = 0;
   long long* stats = nullptr;
   void* ptr = nullptr;
+  bool live = true;   // arena block still held
+  GradView grad;      // training: dL/d(this), set by the backward of its consumers
 };
 typedef std::shared_ptr<Tens> TensP;
 
@@ -69,6 +86,17 @@ class UNet {
   void commit(cudaStream_t s);
   // x: fp32 NCDHW [B][Cin][R^3]; labels: fp32 [B]; out: fp32 NCDHW [B][Cin][R^3]
   void forward(const float* x, const float* labels, float* out, int B, cudaStream_t s);
+  // training engines only. Dropout of the next forward()/backward() pair (p = 0 disables; same seed in both).
+  void set_dropout(float p, unsigned long long seed);
+  // dout: fp32 NCDHW dL/d(out) of the preceding forward() (same x, labels, B). grads: flat fp32 buffer holding the
+  // gradient of every parameter in table order (params()[i] at the sum of the numels before it); entries of
+  // non-trainable tensors (mask, coords, pos_layer.weight) are left untouched. accumulate: += instead of =.
+  void backward(const float* dout, float* grads, int B, bool accumulate, cudaStream_t s);
+  long long grad_offset(const std::string& name) const;
+  long long total_param_numel() const;
+  int num_bwd_steps() const { return (int)bwd_steps_.size(); }
+  double bwd_flops_per_sample() const { return bwd_flops_ / cfg_.max_batch; }
+  std::vector<std::pair<std::string, float>> profile_backward(const float* dout, float* grads, int B, cudaStream_t s);
   double flops_per_sample() const { return flops_ / cfg_.max_batch; }
   size_t arena_bytes() const { return arena_bytes_; }
   int num_gemm_launches() const { return (int)gemms_.size(); }
@@ -115,7 +143,42 @@ class UNet {
   struct Scratch { int S = 1; size_t off = 0; float* ptr = nullptr; bool active = false; };
   Scratch split_begin(int R, int N, int cin_total, int taps);
   void split_end(Scratch& s);
-  TensP gn(const std::string& pname, const std::vector<TensP>& ins, bool silu);
+  TensP gn(const std::string& pname, const std::vector<TensP>& ins, bool silu, int drop_layer = -1);
+  // ---- training plan (unet_train.cu)
+  bool train_ = false;
+  std::vector<std::function<void()>> tape_;  // backward emitters, pushed in forward order, run in reverse
+  std::vector<Step> bwd_steps_;
+  std::vector<std::unique_ptr<GemmOp>> bwd_gemms_;
+  std::vector<std::unique_ptr<WgradOp>> wgrads_;
+  double bwd_flops_ = 0;
+  std::map<std::string, long long> goff_;
+  float* rt_grads_ = nullptr; const float* rt_dout_ = nullptr; bool rt_accum_ = false;
+  int rt_drop_thresh_ = 0; float rt_drop_scale_ = 1.f; unsigned long long rt_seed_ = 0;
+  float* d_dense_out_ = nullptr;  // [mb][dense_total] gradient of the time-embedding projections
+  void add_bwd(const std::string& name, std::function<void(cudaStream_t, int)> fn) { if (!dry_) bwd_steps_.push_back({name, fn}); }
+  void free_act(const TensP& t);
+  GradView new_grad(int C, int R);
+  GradView grad_view(const GradView& g, int c0, int C);
+  void unref(GradView& g);
+  Act act_of_grad(const GradView& g, int R) const;
+  long long G(const std::string& name) const;  // offset of a parameter's gradient in the flat buffer
+  struct Tmp { size_t off = 0; void* ptr = nullptr; };
+  Tmp tmp_alloc(size_t bytes);
+  void tmp_free(Tmp& t);
+  GemmOp* new_bwd_gemm(const std::string& name);
+  void emit_colsum(const std::string& name, const GradView& t, int R, float* per, long long per_ld, long long g0, long long g1, long long g2);
+  void emit_wgrad(const std::string& name, const Act& dy, const Act& x, int ksize, int stride, long long goff, const WgradOut& layout);
+  GradView emit_conv_dgrad(const std::string& name, const GradView& dy, int R, const float* w, int cin_total, const GradView* addend);
+  GradView emit_pointwise(const std::string& name, const std::vector<Act>& srcs, const std::vector<WSrc>& ws, int N, int R, const GradView* addend);
+  GradView emit_gn_backward(const std::string& pname, const std::vector<TensP>& ins, const GradView& da, bool silu, int drop_layer,
+                            const GradView* add0, const GradView* add1);
+  void tape_resblock(const std::vector<TensP>& ins, TensP a, TensP h, TensP a2, TensP out, int out_ch, int midx, int doff);
+  void tape_attn(TensP x, TensP hn, TensP qkv, TensP S, TensP O, TensP out, int midx);
+  void tape_downsample(TensP x, TensP out, int midx);
+  void tape_upsample(TensP x, TensP up, TensP out, int midx);
+  void tape_stem(TensP h0, void* Am, int Kpad, int Kpad_m);
+  void tape_head(TensP h, TensP a, const std::string& gn_name, const std::string& conv_name);
+  void tape_temb();
   TensP resblock(const std::vector<TensP>& ins, int out_ch, int midx);
   TensP attn(const TensP& x, int midx);
   TensP downsample(const TensP& x, int midx);

@@ -27,7 +27,7 @@ def optimization_manager(config):
             for group in optimizer.param_groups:
                 group["lr"] = lr * np.minimum(step / warmup, 1.0)
         if grad_clip >= 0:
-            torch.nn.utils.clip_grad_norm_(params, max_norm=grad_clip)
+            torch.nn.utils.clip_grad_norm_(list(params), max_norm=grad_clip)
         optimizer.step()
 
     return optimize_fn
@@ -69,10 +69,6 @@ def get_step_fn(sde, train, optimize_fn=None, mask=None, loss_type="l2"):
             if clear_grad:
                 optimizer.zero_grad()
             loss = loss_fn(model, batch)
-            if not loss.requires_grad:
-                raise NotImplementedError(
-                    "the sm_100a engine does not provide the backward pass yet (round 1 covers the sampling path); "
-                    "training through this step_fn is not available and there is deliberately no PyTorch fallback")
             loss.backward()
             if update_param:
                 optimize_fn(optimizer, model.parameters(), step=state["step"])

@@ -30,7 +30,7 @@ def arch_from_config(config):
     )
 
 
-def _config_c(arch, max_batch, precision):
+def _config_c(arch, max_batch, precision, training=False):
     c = _native.UNetConfigC()
     c.image_size, c.nf, c.n_levels = arch["image_size"], arch["nf"], len(arch["ch_mult"])
     for i, v in enumerate(arch["ch_mult"]):
@@ -42,6 +42,7 @@ def _config_c(arch, max_batch, precision):
     c.num_channels, c.stem_ksize = arch["num_channels"], arch["stem_ksize"]
     c.use_pos_bias = 1 if arch["use_pos_bias"] else 0
     c.max_batch, c.precision = max_batch, {"bf16": 0, "tf32": 1}[precision]
+    c.training = 1 if training else 0
     return c
 
 
@@ -74,6 +75,25 @@ def variance_scaling_uniform(shape, scale=1.0, generator=None):
     return (torch.rand(shape, generator=generator) * 2.0 - 1.0) * bound
 
 
+class _ScoreNetFn(torch.autograd.Function):
+    """Autograd node of the whole score network: forward and backward both run inside the native engine, so the stock
+    `loss.backward()` of the reference's step_fn (losses.py:104-139) works unchanged. Parameter gradients are written
+    by the engine straight into the module's flat fp32 gradient buffer (`p.grad` are views of it)."""
+
+    @staticmethod
+    def forward(ctx, net, x, labels, *params):
+        out = net._train_forward(x, labels)
+        ctx.net = net
+        ctx.save_for_backward(x, labels)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, labels = ctx.saved_tensors
+        ctx.net._train_backward(x, labels, dout)
+        return (None, None, None) + (None,) * len(ctx.net._trainable)
+
+
 class _Scope(nn.Module):
     """Plain container so dotted parameter names become nested state-dict keys."""
 
@@ -87,6 +107,9 @@ class ScoreNet(nn.Module):
             raise ValueError("config.model.compute_dtype must be 'bf16' or 'tf32'")
         self.max_batch = int(config.model.get("engine_max_batch", 0) or 0) if hasattr(config.model, "get") else 0
         self.scale_by_sigma = bool(config.model.scale_by_sigma)
+        self.dropout = float(config.model.get("dropout", 0.0)) if hasattr(config.model, "get") else 0.0
+        self._train_handle, self._train_batch, self._train_synced = None, 0, None
+        self._flat_grad, self._drop_calls, self._pending = None, 0, None
         # same buffer as the reference (ddpm_res64.py:44): float64 [num_scales]
         self.register_buffer("sigmas", torch.tensor(utils.get_sigmas(config)))
         self._names = []
@@ -109,6 +132,7 @@ class ScoreNet(nn.Module):
         self._handle = None
         self._engine_batch = 0
         self._synced = None
+        self._trainable = [n for n in self._names if n not in ("mask", "coords")]
 
     # ---- parameter plumbing -------------------------------------------------------------------------------------
     def _initial_value(self, name, shape, head_idx):
@@ -159,6 +183,106 @@ class ScoreNet(nn.Module):
         if self._handle is not None:
             _native.lib().mdb_unet_destroy(self._handle)
             self._handle = None
+        if getattr(self, "_train_handle", None) is not None:
+            _native.lib().mdb_unet_destroy(self._train_handle)
+            self._train_handle = None
+
+    # ---- training engine (bf16 operands, fp32 master parameters and gradients) ------------------------------------
+    def _ensure_train_engine(self, batch, device):
+        L = _native.lib()
+        if self._train_handle is not None and batch <= self._train_batch:
+            return
+        if device.type != "cuda":
+            raise _native.NativeError("the score network trains only on a CUDA (sm_100a) device; there is no CPU path")
+        if self._train_handle is not None:
+            L.mdb_unet_destroy(self._train_handle)
+            self._train_handle = None
+        cfg = _config_c(self.arch, batch, "bf16", training=True)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _native.check(L.mdb_unet_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._train_handle, self._train_batch, self._train_synced = h, batch, None
+        numel = ctypes.c_longlong()
+        _native.check(L.mdb_unet_train_info(h, None, None, ctypes.byref(numel)))
+        if self._flat_grad is None or self._flat_grad.numel() != numel.value or self._flat_grad.device != device:
+            self._flat_grad = torch.zeros(numel.value, dtype=torch.float32, device=device)
+            self._grad_views = {}
+            for n in self._trainable:
+                off = ctypes.c_longlong()
+                _native.check(L.mdb_unet_grad_offset(h, n.encode(), ctypes.byref(off)))
+                p = self._param(n)
+                self._grad_views[n] = self._flat_grad[off.value:off.value + p.numel()].view(p.shape)
+
+    def _push_parameters(self, handle, synced):
+        """set_param for every tensor whose fingerprint differs from `synced`, then commit. Returns the fingerprints."""
+        L = _native.lib()
+        fp = self._fingerprints()
+        changed = None if synced is None else (fp != synced).nonzero().flatten().tolist()
+        if changed is not None and not changed:
+            return fp
+        stream = _native.current_stream()
+        for i, n in enumerate(self._names):
+            if changed is not None and i not in changed:
+                continue
+            src = self._param(n).detach().float().contiguous()
+            _native.check(L.mdb_unet_set_param(handle, n.encode(), _native.ptr(src), src.numel(), 1 if src.is_cuda else 0, stream))
+        torch.cuda.current_stream().synchronize()
+        _native.check(L.mdb_unet_commit(handle, stream))
+        return fp
+
+    def _train_forward(self, x, labels):
+        L = _native.lib()
+        B = x.shape[0]
+        with torch.cuda.device(x.device):
+            self._ensure_train_engine(B, x.device)
+            self._train_synced = self._push_parameters(self._train_handle, self._train_synced)
+            p = self.dropout if self.training else 0.0
+            self._drop_calls += 1
+            seed = (torch.initial_seed() * 1000003 + self._drop_calls) & 0xFFFFFFFFFFFFFFFF
+            _native.check(L.mdb_unet_set_dropout(self._train_handle, p, seed))
+            out = torch.empty_like(x)
+            _native.check(L.mdb_unet_forward(self._train_handle, _native.ptr(x), _native.ptr(labels), _native.ptr(out), B,
+                                             _native.current_stream()))
+        self._pending = (x.data_ptr(), B)
+        return out
+
+    def _train_backward(self, x, labels, dout):
+        """Engine backward of the LAST forward (its activations live in the engine's arena); gradients go into the flat
+        buffer: overwritten when every p.grad is None (after zero_grad), accumulated when they are the buffer's views."""
+        L = _native.lib()
+        B = x.shape[0]
+        if self._pending != (x.data_ptr(), B):
+            raise _native.NativeError("backward() must follow the forward() it differentiates: the engine keeps the "
+                                      "activations of one forward pass at a time")
+        params = [self._param(n) for n in self._trainable]
+        none = [p.grad is None for p in params]
+        ours = [p.grad is not None and p.grad.data_ptr() == self._grad_views[n].data_ptr() for p, n in zip(params, self._trainable)]
+        dout = dout.float().contiguous()
+        with torch.cuda.device(x.device):
+            if all(none) or all(ours):
+                _native.check(L.mdb_unet_backward(self._train_handle, _native.ptr(dout), _native.ptr(self._flat_grad),
+                                                  self._flat_grad.numel(), B, 0 if all(none) else 1, _native.current_stream()))
+                if all(none):
+                    for p, n in zip(params, self._trainable):
+                        p.grad = self._grad_views[n]
+            else:  # gradients owned by someone else: compute into a scratch buffer and add
+                tmp = torch.zeros_like(self._flat_grad)
+                _native.check(L.mdb_unet_backward(self._train_handle, _native.ptr(dout), _native.ptr(tmp), tmp.numel(), B, 0,
+                                                  _native.current_stream()))
+                for p, n in zip(params, self._trainable):
+                    v = self._grad_views[n]
+                    g = tmp[v.storage_offset():v.storage_offset() + v.numel()].view(p.shape)
+                    p.grad = g.clone() if p.grad is None else p.grad + g
+        self._pending = None
+
+    def allreduce_grads(self):
+        """Data-parallel training: ONE all-reduce (mean) of the flat gradient buffer over NCCL, replacing the reference's
+        nn.DataParallel gather (models/utils.py:95). No-op without an initialised process group."""
+        import torch.distributed as dist
+        if self._flat_grad is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+        self._flat_grad.mul_(1.0 / dist.get_world_size())
 
     def __del__(self):
         try:
@@ -225,6 +349,11 @@ class ScoreNet(nn.Module):
         x = x.float().contiguous()
         labels = labels.to(device=x.device, dtype=torch.float32).contiguous()
         B = x.shape[0]
+        if torch.is_grad_enabled() and any(self._param(n).requires_grad for n in self._trainable):
+            out = _ScoreNetFn.apply(self, x, labels, *[self._param(n) for n in self._trainable])
+            if self.scale_by_sigma:
+                out = out / self.sigmas.to(out.device)[labels.long(), None, None, None, None].float()
+            return out
         with torch.cuda.device(x.device):
             self._ensure_engine(B, x.device)
             self.sync_parameters()

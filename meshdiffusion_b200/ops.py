@@ -69,3 +69,34 @@ def sampler_update(eps, x, noise, mask, beta, std, seed=0, offset=0):
                                        _native.ptr(mask), float(beta), float(std), V, C, B, seed, offset,
                                        _native.current_stream()))
     return x, x_mean
+
+
+def conv3d_backward(dy, x, weight, stride=1, want_dw=True, want_dx=True):
+    """bf16 NDHWC conv3d backward: dy [B,Zo,Yo,Xo,Cout], x [B,Z,Y,X,Cin], weight fp32 OIDHW -> (dw fp32 OIDHW, dx bf16)."""
+    L = _native.lib()
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    B, Z, Y, X, Cin = x.shape
+    Cout, k = weight.shape[0], weight.shape[2]
+    w = weight.detach().float().contiguous()
+    dw = torch.zeros_like(w) if want_dw else None
+    dx = torch.empty_like(x) if want_dx else None
+    _native.check(L.mdb_conv3d_backward(_native.ptr(dy), _native.ptr(x), _native.ptr(w), B, Cin, Cout, Z, Y, X, k, stride,
+                                        _native.ptr(dw), _native.ptr(dx), _native.current_stream()))
+    return dw, dx
+
+
+def groupnorm_act_backward(x, stats, gamma, beta, da, add=None, silu=True, dropout_p=0.0, seed=0):
+    """Backward of groupnorm_act (bf16): returns (dx bf16 [B,...,C], dgamma fp32 [C], dbeta fp32 [C])."""
+    L = _native.lib()
+    B, C = x.shape[0], x.shape[-1]
+    V = x.numel() // (B * C)
+    stats = torch.round(stats.double() * 16777216.0).to(torch.int64).contiguous()
+    g = gamma.detach().float().contiguous()
+    bt = beta.detach().float().contiguous()
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32)
+    db = torch.empty(C, device=x.device, dtype=torch.float32)
+    _native.check(L.mdb_groupnorm_act_backward(_native.ptr(x), _native.ptr(stats), _native.ptr(g), _native.ptr(bt), _native.ptr(da),
+                                               _native.ptr(add), _native.ptr(dx), _native.ptr(dg), _native.ptr(db), B, V, C,
+                                               1 if silu else 0, float(dropout_p), int(seed), _native.current_stream()))
+    return dx, dg, db

@@ -1,0 +1,215 @@
+"""Training path parity on the GPU: the tcgen05 weight-gradient kernel, the data-gradient convolutions, GroupNorm
+backward and the whole score-network backward, against torch autograd in true fp32 (the reference computes its
+gradients with `loss.backward()`, lib/diffusion/losses.py:104-139).
+
+bf16 operands: the kernels see bf16-rounded inputs, which the fp32 autograd reference is given too, so weight
+gradients (fp32 accumulation) agree to ~1e-4; bf16-stored activation gradients to bf16 resolution.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import build_model, rel_l2, rel_max, tiny_config
+from oracle import synth, unet_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndhwc(t):
+    return t.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+
+
+CONV_CASES = [
+    # (B, Cin, Cout, R, k, stride)
+    (2, 64, 128, 16, 3, 1),    # (8,16,1,1) tiles, halo reuse, one Cout tile
+    (1, 256, 128, 16, 3, 1),   # two Cin tiles
+    (3, 128, 256, 8, 3, 1),    # (8,8,2,1) tiles, per-tap loads
+    (3, 128, 128, 4, 3, 1),    # (4,4,4,2) tiles, odd batch -> half-empty tile
+    (2, 32, 32, 16, 3, 1),     # channel chunks padded by TMA zero fill
+    (2, 128, 128, 16, 3, 2),   # Downsample: stride 2, parity sub-grids
+    (3, 96, 64, 4, 1, 1),      # pointwise, 192 rows (partial last tile)
+    (2, 128, 512, 8, 1, 1),    # pointwise, 4 Cout tiles
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,R,k,stride", CONV_CASES)
+def test_conv3d_backward(B, Cin, Cout, R, k, stride):
+    from meshdiffusion_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Cin + R)
+    x = torch.randn(B, Cin, R, R, R, device="cuda", generator=g).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, k, device="cuda", generator=g) / (Cin * k ** 3) ** 0.5).requires_grad_(True)
+    wq = w.detach().bfloat16().float()
+    if stride == 1:
+        y = F.conv3d(x, w, None, padding=k // 2)
+    else:
+        y = F.conv3d(F.pad(x, (0, 1, 0, 1, 0, 1)), w, None, stride=2)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16().float()
+    y.backward(dy)
+    want_dx = stride == 1
+    dw, dx = ops.conv3d_backward(_ndhwc(dy), _ndhwc(x.detach()), w.detach(), stride=stride, want_dx=want_dx)
+    e_w = rel_max(dw, w.grad)
+    print(f"wgrad B{B} {Cin}->{Cout} R{R} k{k} s{stride}: max {e_w:.3e}")
+    assert e_w < 2e-4
+    if want_dx:
+        # the kernel multiplies by bf16-rounded weights: reference data gradient with the same rounding
+        xr = x.detach().clone().requires_grad_(True)
+        F.conv3d(xr, wq, None, padding=k // 2).backward(dy)
+        got = dx.float().permute(0, 4, 1, 2, 3)
+        e_x = rel_max(got, xr.grad)
+        print(f"dgrad: max {e_x:.3e}")
+        assert e_x < 6e-3
+
+
+@pytest.mark.parametrize("C,R,B,silu,with_add", [(128, 16, 2, True, False), (32, 8, 3, True, True), (384, 8, 2, False, True), (1024, 4, 2, True, False)])
+def test_groupnorm_act_backward(C, R, B, silu, with_add):
+    from meshdiffusion_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(C + R)
+    x = (torch.randn(B, C, R, R, R, device="cuda", generator=g) * 1.5 + 0.3).bfloat16().float().requires_grad_(True)
+    gamma = (torch.rand(C, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    y = F.group_norm(x, 32, gamma, beta, eps=1e-6)
+    if silu:
+        y = F.silu(y)
+    da = torch.randn(y.shape, device="cuda", generator=g).bfloat16().float()
+    y.backward(da)
+    add = torch.randn(x.shape, device="cuda", generator=g).bfloat16().float() if with_add else None
+    xl = _ndhwc(x.detach())
+    xd = xl.double().reshape(B, -1, C)
+    stats = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1)
+    dx, dg, db = ops.groupnorm_act_backward(xl, stats, gamma.detach(), beta.detach(), _ndhwc(da), _ndhwc(add) if with_add else None, silu=silu)
+    ref_dx = x.grad + (add if with_add else 0)
+    e = rel_max(dx.float().permute(0, 4, 1, 2, 3), ref_dx)
+    eg, eb = rel_max(dg, gamma.grad), rel_max(db, beta.grad)
+    print(f"gn bwd C{C} R{R}: dx {e:.3e} dgamma {eg:.3e} dbeta {eb:.3e}")
+    assert e < 1e-2 and eg < 2e-3 and eb < 2e-3
+
+
+def test_groupnorm_dropout_consistency():
+    """The backward dropout mask is the forward one: gradient is zero exactly where the forward output was dropped."""
+    import ctypes
+    from meshdiffusion_b200 import ops
+    C, R, B = 64, 8, 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, R, R, R, C, device="cuda", generator=g).bfloat16()
+    xd = x.double().reshape(B, -1, C)
+    stats = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1)
+    gamma, beta = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    da = torch.ones_like(x)
+    dx0, _, db0 = ops.groupnorm_act_backward(x, stats, gamma, beta, da, silu=False, dropout_p=0.0)
+    dx1, _, db1 = ops.groupnorm_act_backward(x, stats, gamma, beta, da, silu=False, dropout_p=0.25, seed=77)
+    # dbeta = sum of dy = (kept / (1-p)) count: keep fraction ~ 0.75
+    keep = (db1 / db0 * 0.75).mean().item()
+    print(f"dropout keep fraction {keep:.4f}")
+    assert abs(keep - 0.75) < 0.02
+
+
+def _oracle_grads(cfg, sd, x, labels, noise, mask):
+    """fp32 autograd through the oracle network with the reference's DDPM loss (losses.py:69-78)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdg = {k: (v.cuda().clone().requires_grad_(True) if v.dtype == torch.float32 and k not in ("mask", "coords") else v.cuda()) for k, v in sd.items()}
+    arch = unet_oracle.arch_from_config(cfg)
+    pred = unet_oracle.unet_forward(sdg, arch, x, labels)
+    losses = torch.square(pred - noise) * mask
+    losses = losses.reshape(losses.shape[0], -1).mean(dim=-1)
+    loss = torch.mean(losses) / mask.sum() * mask.numel()
+    loss.backward()
+    return loss.detach(), pred.detach(), {k: v.grad for k, v in sdg.items() if v.dtype == torch.float32 and v.requires_grad and v.grad is not None}
+
+
+@pytest.mark.parametrize("name", ["res64", "res128"])
+def test_unet_backward_matches_autograd(name):
+    cfg = tiny_config(name, "bf16")
+    cfg.model.dropout = 0.0
+    model, sd = build_model(cfg, "cuda:0", 21)
+    net = model.module
+    R, B = cfg.data.image_size, 2
+    x, labels = synth.synthetic_inputs(R, B, 31, sd["mask"])
+    x, labels = x.cuda(), labels.cuda()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    noise = torch.randn(x.shape, device="cuda", generator=gen)
+    mask = sd["mask"].cuda().view(1, 1, R, R, R)
+    ref_loss, ref_pred, ref = _oracle_grads(cfg, sd, x, labels, noise, mask)
+
+    net.train()
+    pred = model(x, labels)
+    losses = (torch.square(pred - noise) * mask).reshape(B, -1).mean(dim=-1)
+    loss = torch.mean(losses) / mask.sum() * mask.numel()
+    loss.backward()
+    print(f"{name}: loss {loss.item():.6f} vs {ref_loss.item():.6f}; pred rel-l2 {rel_l2(pred.detach(), ref_pred):.3e}")
+    assert abs(loss.item() - ref_loss.item()) < 3e-2 * abs(ref_loss.item())
+    worst, tot_num, tot_den = ("", 0.0), 0.0, 0.0
+    checked = 0
+    for n, p in net.named_parameters():
+        if n in ("mask", "coords") or n not in ref:
+            continue
+        assert p.grad is not None, n
+        gr = ref[n]
+        num = (p.grad - gr).double().pow(2).sum().item()
+        den = gr.double().pow(2).sum().item()
+        tot_num += num; tot_den += den
+        if den > 0:
+            e = (num / den) ** 0.5
+            if e > worst[1]:
+                worst = (n, e)
+            checked += 1
+        else:
+            assert p.grad.abs().max().item() == 0.0, f"{n}: reference gradient is exactly zero"
+    glob = (tot_num / tot_den) ** 0.5
+    print(f"{name}: {checked} tensors, global rel-l2 {glob:.3e}, worst {worst[0]} {worst[1]:.3e}")
+    assert glob < 3e-2 and worst[1] < 1e-1
+
+
+def test_unet_backward_accumulates_and_is_deterministic():
+    cfg = tiny_config("res64", "bf16")
+    cfg.model.dropout = 0.0
+    model, sd = build_model(cfg, "cuda:0", 3)
+    net = model.module
+    net.train()
+    R, B = 16, 2
+    x, labels = synth.synthetic_inputs(R, B, 8, sd["mask"])
+    x, labels = x.cuda(), labels.cuda()
+
+    def run():
+        out = model(x, labels)
+        out.square().mean().backward()
+
+    run()
+    g1 = net._flat_grad.clone()
+    for p in net.parameters():
+        p.grad = None
+    run()
+    assert torch.equal(g1, net._flat_grad), "gradients differ run to run"
+    run()  # second micro-batch without zero_grad: accumulation (losses.py:111-113)
+    assert torch.allclose(net._flat_grad, 2 * g1, rtol=1e-5, atol=1e-8)
+
+
+def test_train_step_fn_reduces_loss():
+    """The reference's step_fn / optimize_fn / EMA loop runs unchanged on the engine: a few steps on one batch."""
+    from meshdiffusion_b200.diffusion import losses, sde_lib
+    from meshdiffusion_b200.diffusion.models import ema as ema_lib
+    cfg = tiny_config("res64", "bf16")
+    cfg.model.dropout = 0.1
+    cfg.optim.lr = 2e-4
+    cfg.optim.warmup = 0
+    torch.manual_seed(0)
+    model, sd = build_model(cfg, "cuda:0", 9)
+    net = model.module
+    R, B = 16, 4
+    mask = sd["mask"].cuda().view(1, 1, R, R, R)
+    sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda:0")
+    optimizer = losses.get_optimizer(cfg, model.parameters())
+    ema = ema_lib.ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    state = dict(optimizer=optimizer, model=model, ema=ema, step=0)
+    step_fn = losses.get_step_fn(sde, train=True, optimize_fn=losses.optimization_manager(cfg), mask=mask)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    batch = torch.randn(B, 4, R, R, R, device="cuda", generator=g).clamp(-1, 1) * mask
+    first = []
+    for it in range(12):
+        first.append(step_fn(state, batch)["loss"].item())
+    print("losses:", " ".join(f"{v:.4f}" for v in first))
+    assert all(torch.isfinite(torch.tensor(first)))
+    assert sum(first[-4:]) / 4 < sum(first[:4]) / 4, "loss did not go down"
+    assert state["step"] == 12
