@@ -4,10 +4,12 @@ Host loop with the reference's structure: model / EMA / Adam, auto-resume from `
 grid mask written into `score_model.module.mask`, micro-batching through `training.iter_size`, logging every
 `log_freq`, pre-emption checkpoint every `snapshot_freq_for_preemption`, numbered checkpoints every `snapshot_freq`.
 
-Round-1 status: the sm_100a engine has no backward pass yet, so `step_fn(train=True)` raises NotImplementedError at
-the first step (there is deliberately no PyTorch fallback). The loop below is otherwise complete and is what the
-backward kernels will plug into. `config.data.synthetic = True` trains on on-device synthetic DMTet grids
-(sphere SDF on the tet vertices + random near-surface deformation) instead of the dataset.
+Forward AND backward of the score network run inside the sm_100a engine (bf16 operands, fp32 master weights /
+gradients / Adam / EMA); `loss.backward()` reaches it through one autograd node (models/ddpm.py). Data parallelism is
+one process per GPU (torchrun): every rank steps on its own batch shard and the flat fp32 gradient buffer is
+all-reduced (mean) over NCCL once per optimiser step, replacing the reference's nn.DataParallel (models/utils.py:95).
+`config.data.synthetic = True` trains on on-device synthetic DMTet grids (sphere SDF on the tet vertices + random
+near-surface deformation) instead of the dataset.
 """
 import logging
 import os
@@ -37,10 +39,22 @@ def synthetic_grids(batch, resolution, device, generator=None):
     return x
 
 
+def _init_distributed(device):
+    """(rank, world): joins the NCCL group when launched under torchrun, else (0, 1)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl" if torch.device(device).type == "cuda" else "gloo")
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+
+
 def train(config):
     workdir = config.training.train_dir
     os.makedirs(workdir, exist_ok=True)
     device = config.device
+    rank, world = _init_distributed(device)
     score_model = mutils.create_model(config)
     ema = ExponentialMovingAverage(score_model.parameters(), decay=config.model.ema_rate)
     optimizer = losses.get_optimizer(config, score_model.parameters())
@@ -61,7 +75,12 @@ def train(config):
         raise NotImplementedError(f"SDE {config.training.sde} unknown.")
     sde = sde_lib.VPSDE(beta_min=config.model.beta_min, beta_max=config.model.beta_max, N=config.model.num_scales,
                         device=device)
-    optimize_fn = losses.optimization_manager(config)
+    base_optimize_fn = losses.optimization_manager(config)
+
+    def optimize_fn(optimizer, params, step, **kw):
+        score_model.module.allreduce_grads()  # no-op on one GPU
+        base_optimize_fn(optimizer, params, step=step, **kw)
+
     train_step_fn = losses.get_step_fn(sde, train=True, optimize_fn=optimize_fn, mask=mask,
                                        loss_type=config.training.loss_type)
 
@@ -78,8 +97,10 @@ def train(config):
             loss = train_step_fn(state, batch, clear_grad=(inner == 0), update_param=(inner == iter_size - 1))["loss"]
             tmp_loss += loss.item()
         tmp_loss /= iter_size
-        if step % config.training.log_freq == 0:
+        if step % config.training.log_freq == 0 and rank == 0:
             logging.info("step: %d, training_loss: %.5e", step, tmp_loss)
+        if rank != 0:
+            continue  # replicas are identical after the gradient all-reduce: rank 0 alone writes checkpoints
         if step != 0 and step % config.training.snapshot_freq_for_preemption == 0:
             save_checkpoint(checkpoint_meta_dir, state)
         if step != 0 and step % config.training.snapshot_freq == 0 or step == config.training.n_iters:

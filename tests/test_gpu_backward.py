@@ -140,8 +140,7 @@ def test_unet_backward_matches_autograd(name):
     loss.backward()
     print(f"{name}: loss {loss.item():.6f} vs {ref_loss.item():.6f}; pred rel-l2 {rel_l2(pred.detach(), ref_pred):.3e}")
     assert abs(loss.item() - ref_loss.item()) < 3e-2 * abs(ref_loss.item())
-    worst, tot_num, tot_den = ("", 0.0), 0.0, 0.0
-    checked = 0
+    rows, tot_num, tot_den = [], 0.0, 0.0
     for n, p in net.named_parameters():
         if n in ("mask", "coords") or n not in ref:
             continue
@@ -150,15 +149,21 @@ def test_unet_backward_matches_autograd(name):
         num = (p.grad - gr).double().pow(2).sum().item()
         den = gr.double().pow(2).sum().item()
         tot_num += num; tot_den += den
-        if den > 0:
-            e = (num / den) ** 0.5
-            if e > worst[1]:
-                worst = (n, e)
-            checked += 1
-        else:
-            assert p.grad.abs().max().item() == 0.0, f"{n}: reference gradient is exactly zero"
+        rows.append((n, num, den, p.grad.double().pow(2).sum().item()))
     glob = (tot_num / tot_den) ** 0.5
-    print(f"{name}: {checked} tensors, global rel-l2 {glob:.3e}, worst {worst[0]} {worst[1]:.3e}")
+    # Tensors whose true gradient vanishes (pos_layer.weight sees coords*0; the attention KEY bias NIN_1.b shifts every
+    # logit of a row equally, which softmax ignores) carry only rounding noise in the fp32 reference: they are checked
+    # for being negligible, the others for their relative error.
+    checked, worst = 0, ("", 0.0)
+    for n, num, den, ours in rows:
+        if den < 1e-10 * tot_den:
+            assert ours < 1e-6 * tot_den, f"{n}: gradient should vanish, got norm^2 {ours:.3e} of {tot_den:.3e}"
+            continue
+        e = (num / den) ** 0.5
+        checked += 1
+        if e > worst[1]:
+            worst = (n, e)
+    print(f"{name}: {checked}/{len(rows)} tensors, global rel-l2 {glob:.3e}, worst {worst[0]} {worst[1]:.3e}")
     assert glob < 3e-2 and worst[1] < 1e-1
 
 
