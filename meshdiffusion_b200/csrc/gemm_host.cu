@@ -103,6 +103,8 @@ void GemmOp::enable_splits(int S, float* scratch) {
 
 GemmOp::~GemmOp() {
   if (d_loads) cudaFree(d_loads);
+  if (d_ks2load) cudaFree(d_ks2load);
+  if (d_ks0) cudaFree(d_ks0);
   if (d_wpacked && owns_w) cudaFree(d_wpacked);
 }
 
@@ -328,16 +330,17 @@ __global__ void pack_weights_kernel(const LoadEntry* __restrict__ loads, const i
 
 void GemmOp::repack(cudaStream_t stream) {
   if (b_from_act) return;
-  std::vector<int> ks2load, ks0;
-  for (size_t l = 0; l < loads.size(); ++l) {
-    ks0.push_back((int)ks2load.size());
-    for (int j = 0; j < loads[l].nk; ++j) ks2load.push_back((int)l);
+  if (!d_ks2load) {  // k-step -> load-entry tables of the gather kernel: built once, reused by every re-pack
+    std::vector<int> ks2load, ks0;
+    for (size_t l = 0; l < loads.size(); ++l) {
+      ks0.push_back((int)ks2load.size());
+      for (int j = 0; j < loads[l].nk; ++j) ks2load.push_back((int)l);
+    }
+    MDB_CUDA_CHECK(cudaMalloc(&d_ks2load, ks2load.size() * sizeof(int)));
+    MDB_CUDA_CHECK(cudaMalloc(&d_ks0, ks0.size() * sizeof(int)));
+    MDB_CUDA_CHECK(cudaMemcpy(d_ks2load, ks2load.data(), ks2load.size() * sizeof(int), cudaMemcpyHostToDevice));
+    MDB_CUDA_CHECK(cudaMemcpy(d_ks0, ks0.data(), ks0.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
-  int *d_a = nullptr, *d_b = nullptr;
-  MDB_CUDA_CHECK(cudaMalloc(&d_a, ks2load.size() * sizeof(int)));
-  MDB_CUDA_CHECK(cudaMalloc(&d_b, ks0.size() * sizeof(int)));
-  MDB_CUDA_CHECK(cudaMemcpyAsync(d_a, ks2load.data(), ks2load.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-  MDB_CUDA_CHECK(cudaMemcpyAsync(d_b, ks0.data(), ks0.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   if (wsrcs.size() > 4) throw std::runtime_error("mdb: too many weight sources");
   PackArgs args{};
   for (size_t i = 0; i < wsrcs.size(); ++i) args.w[i] = {wsrcs[i].ptr, wsrcs[i].sn, wsrcs[i].sc, wsrcs[i].st, wsrcs[i].cvalid, wsrcs[i].ndiv, wsrcs[i].sn_hi, wsrcs[i].cdiv, wsrcs[i].sc_hi};
@@ -345,13 +348,10 @@ void GemmOp::repack(cudaStream_t stream) {
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (prec == kTF32)
-    pack_weights_kernel<true><<<blocks, 256, 0, stream>>>(d_loads, d_a, d_b, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+    pack_weights_kernel<true><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
   else
-    pack_weights_kernel<false><<<blocks, 256, 0, stream>>>(d_loads, d_a, d_b, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+    pack_weights_kernel<false><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
   MDB_CUDA_CHECK(cudaGetLastError());
-  MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
-  cudaFree(d_a);
-  cudaFree(d_b);
 }
 
 void GemmOp::finalize(cudaStream_t stream, bool pack) {

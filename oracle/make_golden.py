@@ -89,6 +89,52 @@ def golden_unet_forward(ref):
                             checksum=synth.state_checksum(sd), state_seed=11, input_seed=12)
 
 
+def ddpm_loss(pred, noise, mask):
+    """lib/diffusion/losses.py:69-78 (l2, masked)."""
+    losses = torch.square(pred - noise) * mask
+    losses = losses.reshape(losses.shape[0], -1).mean(dim=-1)
+    return torch.mean(losses) / mask.sum() * np.prod(mask.size())
+
+
+def grad_signature(name, g, seed=1234):
+    """(L2 norm, 4 seeded random projections) of one gradient tensor -- a compact pin of the whole tensor."""
+    gen = torch.Generator().manual_seed(seed + sum(ord(c) for c in name))
+    r = torch.randn(4, g.numel(), generator=gen, dtype=torch.float64)
+    gd = g.detach().double().reshape(-1)
+    return np.concatenate([[gd.norm().item()], (r @ gd).numpy()])
+
+
+def golden_unet_backward(ref):
+    """Gradients of the reference modules (torch autograd, fp32 CPU) for the DDPM loss on seeded inputs; the oracle's
+    autograd gradients must agree, and the per-tensor signatures are committed for the CPU and GPU parity tests."""
+    for name in ("res64", "res128"):
+        cfg = ref_config(ref, name, tiny=True)
+        model = build_ref_model(ref, cfg)   # eval(): dropout is the identity, as in the 'dropout disabled' parity runs
+        sd = synth.synthetic_state_dict(model.state_dict(), seed=21)
+        model.load_state_dict(sd)
+        R = cfg.data.image_size
+        x, labels = synth.synthetic_inputs(R, batch=2, seed=31, mask=sd["mask"])
+        noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(5))
+        mask = sd["mask"].view(1, 1, R, R, R)
+        loss = ddpm_loss(model(x, labels), noise, mask)
+        loss.backward()
+        ref_g = {n: p.grad for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+        osd = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and k not in ("mask", "coords") else v) for k, v in sd.items()}
+        oloss = ddpm_loss(unet_oracle.unet_forward(osd, unet_oracle.arch_from_config(cfg), x, labels), noise, mask)
+        oloss.backward()
+        tot = sum(g.double().pow(2).sum().item() for g in ref_g.values()) ** 0.5
+        worst = 0.0
+        for n, g in ref_g.items():
+            worst = max(worst, (osd[n].grad - g).double().norm().item() / tot)
+        print(f"unet {name} tiny backward: loss {loss.item():.6f} (oracle {oloss.item():.6f}), {len(ref_g)} gradient tensors, "
+              f"|g| {tot:.4e}, worst oracle-vs-reference diff / |g| {worst:.3e}")
+        assert abs(loss.item() - oloss.item()) < 1e-5 * abs(loss.item()) and worst < 1e-5, "oracle backward disagrees with the reference"
+        names = sorted(ref_g)
+        np.savez_compressed(os.path.join(GOLD, f"unet_tiny_{name}_grads.npz"), loss=loss.item(), names=np.array(names),
+                            sig=np.stack([grad_signature(n, ref_g[n]) for n in names]), total_norm=tot,
+                            state_seed=21, input_seed=31, noise_seed=5)
+
+
 def golden_sampler(ref):
     import tqdm
     cfg = ref_config(ref, "res64", tiny=True)
@@ -209,6 +255,7 @@ if __name__ == "__main__":
     ref = import_reference()
     golden_marching_tets()
     golden_unet_forward(ref)
+    golden_unet_backward(ref)
     golden_sampler(ref)
     golden_param_tables(ref)
     print("golden vectors written to", GOLD)

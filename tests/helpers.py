@@ -49,3 +49,18 @@ def rel_l2(a, b):
 
 def load_golden(name):
     return np.load(os.path.join(GOLD, name))
+
+
+def ddpm_loss(pred, noise, mask):
+    """lib/diffusion/losses.py:69-78 (l2, masked)."""
+    losses = torch.square(pred - noise) * mask
+    losses = losses.reshape(losses.shape[0], -1).mean(dim=-1)
+    return torch.mean(losses) / mask.sum() * mask.numel()
+
+
+def grad_signature(name, g, seed=1234):
+    """Same (norm, 4 random projections) signature as oracle/make_golden.py::grad_signature."""
+    gen = torch.Generator().manual_seed(seed + sum(ord(c) for c in name))
+    r = torch.randn(4, g.numel(), generator=gen, dtype=torch.float64)
+    gd = g.detach().double().reshape(-1).cpu()
+    return np.concatenate([[gd.norm().item()], (r @ gd).numpy()])

@@ -218,3 +218,83 @@ def test_train_step_fn_reduces_loss():
     assert all(torch.isfinite(torch.tensor(first)))
     assert sum(first[-4:]) / 4 < sum(first[:4]) / 4, "loss did not go down"
     assert state["step"] == 12
+
+
+def test_loss_curve_tracks_fp32_reference():
+    """20 optimiser steps with dropout disabled, same data / labels / noise / Adam settings, engine (bf16
+    operands) vs fp32 autograd through the oracle network: the loss curves must stay together."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = tiny_config("res64", "bf16")
+    cfg.model.dropout = 0.0
+    model, sd = build_model(cfg, "cuda:0", 13)
+    net = model.module
+    net.train()
+    R, B, steps = 16, 4, 20
+    mask = sd["mask"].cuda().view(1, 1, R, R, R)
+    arch = unet_oracle.arch_from_config(cfg)
+    ref_sd = {k: (v.cuda().clone().requires_grad_(True) if v.dtype == torch.float32 and k not in ("mask", "coords") else v.cuda()) for k, v in sd.items()}
+    ref_params = [v for v in ref_sd.values() if v.requires_grad]
+    opt_ref = torch.optim.Adam(ref_params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    data = (torch.rand(B, 4, R, R, R, device="cuda", generator=g) * 2 - 1) * mask
+
+    def ddpm_loss(pred, noise):
+        l = (torch.square(pred - noise) * mask).reshape(B, -1).mean(dim=-1)
+        return torch.mean(l) / mask.sum() * mask.numel()
+
+    ours, theirs = [], []
+    for it in range(steps):
+        labels = torch.randint(0, 1000, (B,), device="cuda", generator=g).float()
+        noise = torch.randn(data.shape, device="cuda", generator=g)
+        x = (0.7 * data + 0.7 * noise) * mask
+        opt_ref.zero_grad()
+        lr_ = ddpm_loss(unet_oracle.unet_forward(ref_sd, arch, x, labels), noise)
+        lr_.backward()
+        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        opt_ref.step()
+        opt.zero_grad()
+        lo = ddpm_loss(model(x, labels), noise)
+        lo.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in net.parameters() if p.requires_grad], 1.0)
+        opt.step()
+        ours.append(lo.item()); theirs.append(lr_.item())
+    print("engine:", " ".join(f"{v:.4f}" for v in ours))
+    print("fp32  :", " ".join(f"{v:.4f}" for v in theirs))
+    rel = max(abs(a - b) / abs(b) for a, b in zip(ours, theirs))
+    print(f"max relative loss difference over {steps} steps: {rel:.3e}")
+    assert rel < 5e-2
+    assert theirs[-1] < theirs[0]
+
+
+@pytest.mark.parametrize("name", ["res64", "res128"])
+def test_unet_backward_matches_reference_golden(name):
+    """Engine gradients vs the signatures (norm + 4 random projections per tensor) of the REFERENCE modules' own
+    loss.backward() on CPU fp32 (oracle/make_golden.py::golden_unet_backward)."""
+    import numpy as np
+    from helpers import ddpm_loss, grad_signature, load_golden
+    gold = load_golden(f"unet_tiny_{name}_grads.npz")
+    cfg = tiny_config(name, "bf16")
+    cfg.model.dropout = 0.0
+    model, sd = build_model(cfg, "cuda:0", int(gold["state_seed"]))
+    net = model.module
+    net.train()
+    R = cfg.data.image_size
+    x, labels = synth.synthetic_inputs(R, 2, int(gold["input_seed"]), sd["mask"])
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(int(gold["noise_seed"]))).cuda()
+    loss = ddpm_loss(model(x.cuda(), labels.cuda()), noise, sd["mask"].cuda().view(1, 1, R, R, R))
+    loss.backward()
+    print(f"{name}: loss {loss.item():.6f} vs reference {float(gold['loss']):.6f}")
+    assert abs(loss.item() - float(gold["loss"])) < 2e-2 * float(gold["loss"])
+    tot = float(gold["total_norm"])
+    params = dict(net.named_parameters())
+    worst = 0.0
+    for n, sig in zip(gold["names"], gold["sig"]):
+        got = grad_signature(str(n), params[str(n)].grad)
+        # a projection of the error onto a unit-variance random vector is ~ N(0, |err|^2): 4 sigma of a 5 % error
+        tol = 4 * (0.05 * sig[0] + 2e-3 * tot)
+        assert abs(got[0] - sig[0]) < 0.1 * sig[0] + 2e-3 * tot, f"{n}: norm {got[0]:.4e} vs {sig[0]:.4e}"
+        assert np.abs(got[1:] - sig[1:]).max() < tol, f"{n}: projections {got[1:]} vs {sig[1:]}"
+        worst = max(worst, np.abs(got[1:] - sig[1:]).max() / tot)
+    print(f"{name}: {len(gold['names'])} tensors, worst projection error / |g| {worst:.3e}")

@@ -80,3 +80,21 @@ def test_ddim_oracle_matches_reference_golden():
     with torch.no_grad():
         xn, x0 = sampler_oracle.ddim_update(sde, fn, xd, torch.full((B,), 0.64), torch.full((B,), 0.6084))
     assert np.abs(xn.numpy() - gold["ddim_x"]).max() < 2e-4 and np.abs(x0.numpy() - gold["ddim_x0"]).max() < 2e-4
+
+
+def test_unet_oracle_backward_matches_reference_golden():
+    """Autograd through the oracle reproduces the gradient signatures of the REFERENCE modules' loss.backward()."""
+    from helpers import ddpm_loss, grad_signature
+    gold = load_golden("unet_tiny_res64_grads.npz")
+    cfg, sd = _tiny_sd("res64", int(gold["state_seed"]))
+    R = cfg.data.image_size
+    x, labels = synth.synthetic_inputs(R, 2, int(gold["input_seed"]), sd["mask"])
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(int(gold["noise_seed"])))
+    osd = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float32 and k not in ("mask", "coords") else v) for k, v in sd.items()}
+    loss = ddpm_loss(unet_oracle.unet_forward(osd, unet_oracle.arch_from_config(cfg), x, labels), noise, sd["mask"].view(1, 1, R, R, R))
+    loss.backward()
+    assert abs(loss.item() - float(gold["loss"])) < 1e-5 * float(gold["loss"])
+    tot = float(gold["total_norm"])
+    for n, sig in zip(gold["names"], gold["sig"]):
+        got = grad_signature(str(n), osd[str(n)].grad)
+        assert np.abs(got - sig).max() < 2e-4 * tot, n
