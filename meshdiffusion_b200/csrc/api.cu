@@ -293,7 +293,7 @@ int mdb_groupnorm_act_backward(const void* x, const long long* stats, const floa
   MDB_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
   float *part = nullptr, *sums = nullptr;
-  MDB_CUDA_CHECK(cudaMalloc(&part, (size_t)kBwdMaxBlocksX * B * C * 2 * sizeof(float)));
+  MDB_CUDA_CHECK(cudaMalloc(&part, (size_t)kBwdPartRows(B) * C * 2 * sizeof(float)));
   MDB_CUDA_CHECK(cudaMalloc(&sums, (size_t)B * C * 2 * sizeof(float)));
   GnBwdArgs a{};
   a.x0 = x; a.C0 = C; a.ld0 = C; a.stats0 = stats; a.gamma = gamma; a.beta = beta; a.da = da;

@@ -35,11 +35,10 @@ __device__ __forceinline__ float dsilu(float y) {
   return s * fmaf(y, 1.f - s, 1.f);
 }
 
-// grid.x for the staged reductions: enough blocks to fill the machine, at most kBwdMaxBlocksX per sample
+// grid.x for the staged reductions: about kBwdTargetBlocks blocks in total (4 x 148 SMs), whatever the batch
 static inline int blocks_x(long long voxels, int k, int B) {
   long long gx = (voxels + (long long)k * 4 - 1) / ((long long)k * 4);
-  long long want = (148LL * 8 + B - 1) / B;
-  if (want > kBwdMaxBlocksX) want = kBwdMaxBlocksX;
+  const long long want = (kBwdTargetBlocks + B - 1) / B;
   if (gx > want) gx = want;
   return gx < 1 ? 1 : (int)gx;
 }
@@ -90,7 +89,8 @@ __device__ __forceinline__ void gn_dy(const GnBwdArgs& a, const float* x, const 
   }
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs a, int cv, int k) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(GnBwdArgs a, int cv, int k) {
+  constexpr int UNROLL = 4;
   __shared__ float red[256 * VEC * 2];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
@@ -110,14 +110,23 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs a, int cv,
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const long long step = (long long)gridDim.x * k;
-  for (long long v = (long long)blockIdx.x * k + vl; v < a.voxels; v += step) {
-    const uint4 rx = __ldg((const uint4*)(src + v * src_stride));
-    const uint4 rd = __ldg((const uint4*)(dsrc + v * d_stride));
-    float x[VEC], da[VEC], xh[VEC], dy[VEC];
-    unpack8(rx, x); unpack8(rd, da);
-    gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+  for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
+    uint4 rx[UNROLL], rd[UNROLL];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], xh[j], s2[j]); }
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long v = v0 + u * step;
+      if (v < a.voxels) { rx[u] = __ldg((const uint4*)(src + v * src_stride)); rd[u] = __ldg((const uint4*)(dsrc + v * d_stride)); }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long v = v0 + u * step;
+      if (v >= a.voxels) continue;
+      float x[VEC], da[VEC], xh[VEC], dy[VEC];
+      unpack8(rx[u], x); unpack8(rd[u], da);
+      gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], xh[j], s2[j]); }
+    }
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { red[(threadIdx.x * VEC + j) * 2] = s1[j]; red[(threadIdx.x * VEC + j) * 2 + 1] = s2[j]; }
@@ -168,7 +177,9 @@ void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s) {
   MDB_LAUNCH_CHECK();
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
+  constexpr int UNROLL = 2;
+  __shared__ float red[256 * VEC];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
   const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
@@ -208,35 +219,76 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, int cv, 
   char* dst = (char*)a.dx + ((long long)b * a.voxels * C + c) * 2;
   const char* p0 = a.add0 ? (const char*)a.add0 + ((long long)b * a.voxels * a.add0_ld + c) * 2 : nullptr;
   const char* p1 = a.add1 ? (const char*)a.add1 + ((long long)b * a.voxels * a.add1_ld + c) * 2 : nullptr;
-  const long long step = (long long)gridDim.x * k;
-  for (long long v = (long long)blockIdx.x * k + vl; v < a.voxels; v += step) {
-    const uint4 rx = __ldg((const uint4*)(src + v * src_stride));
-    const uint4 rd = __ldg((const uint4*)(dsrc + v * d_stride));
-    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-    if (p0) r0 = __ldg((const uint4*)(p0 + v * a.add0_ld * 2));
-    if (p1) r1 = __ldg((const uint4*)(p1 + v * a.add1_ld * 2));
-    float x[VEC], da[VEC], xh[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
-    unpack8(rx, x); unpack8(rd, da); unpack8(r0, e0); unpack8(r1, e1);
-    gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+  float cs[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) o[j] = fmaf(c1[j], dy[j], -m1[j]) - xh[j] * m2[j] + e0[j] + e1[j];
-    *((uint4*)(dst + v * d_stride)) = pack8(o);
+  for (int j = 0; j < VEC; ++j) cs[j] = 0.f;
+  const long long step = (long long)gridDim.x * k;
+  for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
+    uint4 rx[UNROLL], rd[UNROLL], r0[UNROLL], r1[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long v = v0 + u * step;
+      r0[u] = make_uint4(0, 0, 0, 0); r1[u] = make_uint4(0, 0, 0, 0);
+      if (v < a.voxels) {
+        rx[u] = __ldg((const uint4*)(src + v * src_stride));
+        rd[u] = __ldg((const uint4*)(dsrc + v * d_stride));
+        if (p0) r0[u] = __ldg((const uint4*)(p0 + v * a.add0_ld * 2));
+        if (p1) r1[u] = __ldg((const uint4*)(p1 + v * a.add1_ld * 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long v = v0 + u * step;
+      if (v >= a.voxels) continue;
+      float x[VEC], da[VEC], xh[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
+      unpack8(rx[u], x); unpack8(rd[u], da); unpack8(r0[u], e0); unpack8(r1[u], e1);
+      gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        o[j] = fmaf(c1[j], dy[j], -m1[j]) - xh[j] * m2[j] + e0[j] + e1[j];
+        cs[j] += o[j];
+      }
+      *((uint4*)(dst + v * d_stride)) = pack8(o);
+    }
   }
+  if (a.cs_part) {  // per-(sample, channel) column sums of dx for the bias / time-embedding gradients downstream
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = cs[j];
+    __syncthreads();
+    if (vl == 0) {
+      for (int j = 0; j < VEC; ++j) {
+        float t = 0.f;
+        for (int l = 0; l < k; ++l) t += red[(l * cv + cvi) * VEC + j];
+        a.cs_part[((long long)blockIdx.x * gridDim.y + b) * C + c + j] = t;
+      }
+    }
+  }
+}
+
+__global__ void cs_final_kernel(const float* __restrict__ part, float* __restrict__ per, int gx, int BC) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BC) return;
+  float t = 0.f;
+  for (int x = 0; x < gx; ++x) t += part[(long long)x * BC + i];
+  per[i] = t;
 }
 
 void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s) {
   int cv, k;
   gn_launch_shape(a, cv, k);
-  long long gx = (a.voxels + (long long)k * 4 - 1) / ((long long)k * 4);
-  const long long cap = (148LL * 8 + B - 1) / B;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
+  const int C = a.C0 + a.C1;
+  const int gx = blocks_x(a.voxels, k, B);
   gn_bwd_apply_kernel<<<dim3((unsigned)gx, B), cv * k, 0, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
+  if (a.cs_part) {
+    cs_final_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a.cs_part, a.cs_per, gx, B * C);
+    MDB_LAUNCH_CHECK();
+  }
 }
 
 // ------------------------------------------------------------------ column sums (bias / time-embedding gradients)
 __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a, int cv, int k) {
+  constexpr int UNROLL = 4;
   __shared__ float red[256 * VEC];
   const int b = blockIdx.y;
   const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
@@ -246,11 +298,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a, int cv, int k
 #pragma unroll
   for (int j = 0; j < VEC; ++j) s1[j] = 0.f;
   const long long step = (long long)gridDim.x * k;
-  for (long long v = (long long)blockIdx.x * k + vl; v < a.voxels; v += step) {
-    float x[VEC];
-    unpack8(__ldg((const uint4*)(src + v * a.ld * 2)), x);
+  for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
+    uint4 r[UNROLL];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) s1[j] += x[j];
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long v = v0 + u * step;
+      r[u] = make_uint4(0, 0, 0, 0);
+      if (v < a.voxels) r[u] = __ldg((const uint4*)(src + v * a.ld * 2));
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float x[VEC];
+      unpack8(r[u], x);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s1[j] += x[j];
+    }
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = s1[j];
@@ -269,7 +331,8 @@ __global__ void colsum_final_kernel(ColsumArgs a, int gx, int B) {
   float tot = 0.f;
   for (int b = 0; b < B; ++b) {
     float t = 0.f;
-    for (int x = 0; x < gx; ++x) t += a.part[((long long)x * B + b) * a.C + c];
+    if (a.from_per) t = a.part[(long long)b * a.from_ld + c];
+    else for (int x = 0; x < gx; ++x) t += a.part[((long long)x * B + b) * a.C + c];
     if (a.per) a.per[(long long)b * a.per_ld + c] = t;
     tot += t;
   }
@@ -278,6 +341,13 @@ __global__ void colsum_final_kernel(ColsumArgs a, int gx, int B) {
   if (a.total2) a.total2[c] = (a.accumulate ? a.total2[c] : 0.f) + tot;
 }
 void launch_colsum(const ColsumArgs& a, int B, cudaStream_t s) {
+  if (a.from_per) {  // the producer already left per-sample sums ([B][from_ld] floats): only the batch sum remains
+    ColsumArgs c = a;
+    c.part = const_cast<float*>(a.from_per);
+    colsum_final_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(c, 1, B);
+    MDB_LAUNCH_CHECK();
+    return;
+  }
   const int cv = a.C / VEC;
   if (cv < 1 || cv > 256 || a.C % VEC != 0) throw std::runtime_error("mdb: unsupported channel count in colsum");
   const int k = 256 / cv;

@@ -10,8 +10,10 @@
 
 namespace mdb {
 
-// max blocks along the voxel axis of the staged reductions (sizes the partial buffers)
-constexpr int kBwdMaxBlocksX = 64;
+// total block budget of the staged reductions: grid = (ceil(kBwdTargetBlocks / B), B). Partial buffers hold
+// kBwdPartRows(B) rows of C (or 2C) floats.
+constexpr int kBwdTargetBlocks = 592;
+inline int kBwdPartRows(int B) { return kBwdTargetBlocks + B; }
 
 // GroupNorm(32, eps 1e-6) [+SiLU] [+dropout] backward over the channel concatenation of up to two sources.
 //   forward:  y = gamma*xhat + beta, a = drop(act(y));   given da = dL/da  [B][V][C] dense
@@ -34,6 +36,8 @@ struct GnBwdArgs {
   void* dx;                // [B][V][C] dense
   const void* add0; long long add0_ld;
   const void* add1; long long add1_ld;
+  // optional by-product of pass 2: cs_per[b][c] = sum_v dx[b][v][c] (cs_part: [rows][C] block partials)
+  float* cs_part; float* cs_per;
 };
 void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s);  // part -> sums -> dgamma/dbeta
 void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s);
@@ -45,6 +49,7 @@ struct ColsumArgs {
   float* part;                // [gx][B][C] scratch
   float* per; long long per_ld;
   float* total0; float* total1; float* total2; int accumulate;
+  const float* from_per; long long from_ld;  // per-sample sums already computed by the producing kernel ([B][from_ld])
 };
 void launch_colsum(const ColsumArgs& a, int B, cudaStream_t s);
 

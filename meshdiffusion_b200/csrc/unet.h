@@ -54,12 +54,14 @@ class Arena {
 
 // A gradient buffer in the arena, shared by the views handed to the tensors it is the gradient of (the two halves of
 // a channel concatenation); returned to the arena when the last view is dropped.
-struct GradBuf { size_t off = 0; int refs = 0; };
+struct GradBuf { size_t off = 0; int refs = 0; bool has_cs = false; size_t cs_off = 0; };
 struct GradView {
   std::shared_ptr<GradBuf> buf;
   void* ptr = nullptr;
   long long ld = 0;
   int C = 0;
+  float* colsum = nullptr;  // [B][cs_ld] per-sample column sums of this view's channels (left by gn_bwd_apply), or null
+  long long cs_ld = 0;
   bool valid() const { return buf != nullptr; }
 };
 

@@ -29,14 +29,19 @@ GradView UNet::grad_view(const GradView& g, int c0, int C) {
   v.buf->refs++;
   v.ptr = dry_ ? nullptr : (char*)g.ptr + (size_t)c0 * 2;
   v.C = C;
+  if (g.colsum) v.colsum = g.colsum + c0;
   return v;
 }
 
 void UNet::unref(GradView& g) {
   if (!g.buf) return;
-  if (--g.buf->refs == 0) arena_.release(g.buf->off);
+  if (--g.buf->refs == 0) {
+    arena_.release(g.buf->off);
+    if (g.buf->has_cs) arena_.release(g.buf->cs_off);
+  }
   g.buf.reset();
   g.ptr = nullptr;
+  g.colsum = nullptr;
 }
 
 Act UNet::act_of_grad(const GradView& g, int R) const {
@@ -118,11 +123,14 @@ std::vector<std::pair<std::string, float>> UNet::profile_backward(const float* d
 // per[b][c] = sum_v t[b][v][c] (optional) and up to three parameter gradients (offsets, -1 = none) += sum_b per[b][c]
 void UNet::emit_colsum(const std::string& name, const GradView& t, int R, float* per, long long per_ld, long long g0,
                        long long g1, long long g2) {
-  Tmp part = tmp_alloc((size_t)kBwdMaxBlocksX * cfg_.max_batch * t.C * sizeof(float));
+  // when the producing GroupNorm-backward kernel already left per-sample column sums, only the batch sum remains
+  const bool have = t.buf && t.buf->has_cs;
+  Tmp part = tmp_alloc(have ? 16 : (size_t)kBwdPartRows(cfg_.max_batch) * t.C * sizeof(float));
   if (!dry_) {
     ColsumArgs a{};
     a.t = t.ptr; a.ld = t.ld; a.C = t.C; a.voxels = (long long)R * R * R;
     a.part = (float*)part.ptr; a.per = per; a.per_ld = per_ld;
+    a.from_per = t.colsum; a.from_ld = t.cs_ld;
     add_bwd(name, [=](cudaStream_t s, int B) {
       ColsumArgs c = a;
       c.total0 = g0 >= 0 ? rt_grads_ + g0 : nullptr;
@@ -195,9 +203,16 @@ GradView UNet::emit_gn_backward(const std::string& pname, const std::vector<Tens
   float* gamma = P(pname + ".weight", {C});
   float* beta = P(pname + ".bias", {C});
   if (da.ld != C) throw std::runtime_error("mdb: GroupNorm backward needs a dense upstream gradient");
-  Tmp part = tmp_alloc((size_t)kBwdMaxBlocksX * mb * C * 2 * sizeof(float));
+  Tmp part = tmp_alloc((size_t)kBwdPartRows(mb) * C * 2 * sizeof(float));
   Tmp sums = tmp_alloc((size_t)mb * C * 2 * sizeof(float));
   GradView dx = new_grad(C, R);
+  // by-product of the apply pass: per-(sample, channel) sums of dx, kept with the buffer for the bias gradients of
+  // whichever op produced the tensor this is the gradient of
+  dx.buf->has_cs = true;
+  dx.buf->cs_off = arena_.alloc((size_t)mb * C * sizeof(float));
+  dx.colsum = dry_ ? nullptr : reinterpret_cast<float*>(arena_base_ + dx.buf->cs_off);
+  dx.cs_ld = C;
+  Tmp cs_part = tmp_alloc((size_t)kBwdPartRows(mb) * C * sizeof(float));
   if (!dry_) {
     GnBwdArgs a{};
     a.x0 = ins[0]->ptr; a.C0 = ins[0]->C; a.ld0 = ins[0]->C;
@@ -209,6 +224,7 @@ GradView UNet::emit_gn_backward(const std::string& pname, const std::vector<Tens
     a.dx = dx.ptr;
     a.add0 = add0 ? add0->ptr : nullptr; a.add0_ld = add0 ? add0->ld : 0;
     a.add1 = add1 ? add1->ptr : nullptr; a.add1_ld = add1 ? add1->ld : 0;
+    a.cs_part = (float*)cs_part.ptr; a.cs_per = dx.colsum;
     const long long gw = G(pname + ".weight"), gb = G(pname + ".bias");
     auto with_rt = [this, a, gw, gb, drop_layer]() {
       GnBwdArgs c = a;
@@ -224,6 +240,7 @@ GradView UNet::emit_gn_backward(const std::string& pname, const std::vector<Tens
   }
   tmp_free(part);
   tmp_free(sums);
+  tmp_free(cs_part);
   return dx;
 }
 
