@@ -166,6 +166,22 @@ int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batc
                               long long* valid_vert_idx, const long long* vert_off, const long long* face_off,
                               const long long* vv_off, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Mesh post-ops after marching tets. Scatter-adds run as 2^-40 fixed-point integer atomics: results are
+ * independent of face order (bitwise reproducible).
+ */
+/* auto_normals (nvdiffrec/lib/render/mesh.py:200-227): v_pos fp32 [Nv][3], faces int64 [F][3] -> v_nrm fp32 [Nv][3]
+ * (sum of unnormalised face normals, degenerate -> (0,0,1), safe_normalize), f_nrm fp32 [F][3] (nullable).
+ * scratch: device int64 [Nv][3]. */
+int mdb_mesh_auto_normals(const float* v_pos, const long long* faces, int n_verts, int n_faces, float* v_nrm, float* f_nrm,
+                          long long* scratch, void* stream);
+/* compute_tangents (mesh.py:233-277): per-face tangent from positions and texture coordinates, averaged per normal
+ * index, Gram-Schmidt against v_nrm. v_tex fp32 [Nt][2]; index arrays int64 [F][3]; v_nrm fp32 [Nn][3] -> v_tng [Nn][3].
+ * scratch: device bytes Nn*3*8 + Nn*4. */
+int mdb_mesh_compute_tangents(const float* v_pos, const long long* t_pos_idx, const float* v_tex, const long long* t_tex_idx,
+                              const float* v_nrm, const long long* t_nrm_idx, int n_nrm, int n_faces, float* v_tng,
+                              long long* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

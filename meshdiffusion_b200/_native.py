@@ -70,6 +70,8 @@ SIGNATURES = {
     "mdb_marching_tets_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "mdb_marching_tets_uvs": (_i, [_vp, _vp, _vp]),
     "mdb_marching_tets_count": (_i, [_vp, _vp, _i, ctypes.POINTER(_i), _vp]),
+    "mdb_mesh_auto_normals": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "mdb_mesh_compute_tangents": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "mdb_marching_tets_extract": (_i, [_vp, _vp, _ll, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

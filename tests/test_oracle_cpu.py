@@ -98,3 +98,22 @@ def test_unet_oracle_backward_matches_reference_golden():
     for n, sig in zip(gold["names"], gold["sig"]):
         got = grad_signature(str(n), osd[str(n)].grad)
         assert np.abs(got - sig).max() < 2e-4 * tot, n
+
+
+def test_mesh_ops_oracle_matches_reference_golden():
+    """auto_normals / compute_tangents restatement vs the reference functions' output on the synthetic sphere mesh."""
+    from oracle import mesh_oracle
+    from meshdiffusion_b200.geometry import dmtet
+    gold = load_golden("mesh_ops_64.npz")
+    verts, idx = dmtet.load_tet_grid(64)
+    sdf, pos = synth.synthetic_dmtet(verts, seed=int(gold["seed"]), noisy=False)
+    v, f, uvs, uv_idx, _, _ = mt_oracle.marching_tets(pos, sdf, idx)
+    assert v.shape[0] == int(gold["n_verts"]) and f.shape[0] == int(gold["n_faces"])
+    vn, fn = mesh_oracle.auto_normals(v, f)
+    assert np.abs(vn - gold["v_nrm"]).max() < 1e-5
+    assert np.abs(fn.astype(np.float64).sum(0) - gold["f_nrm_sum"]).max() < 1e-6
+    vt = mesh_oracle.compute_tangents(v, f, uvs, uv_idx, vn, f)
+    terr = np.abs(vt - gold["v_tng"]).max(1)
+    assert np.percentile(terr, 99) < 1e-5 and (terr > 1e-3).mean() < 0.01
+    text = mesh_oracle.obj_text(v[:3], f[:2])
+    assert text.splitlines()[0] == "g default" and text.splitlines()[-1].startswith("f  ")
