@@ -138,3 +138,37 @@ def test_world_size_2_gloo_plumbing(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("RANK_OK") == 2
+
+
+GLOO_TRAIN_CHILD = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+from helpers import tiny_config
+from meshdiffusion_b200.diffusion.models import utils as mutils
+cfg = tiny_config("res64", "bf16")
+cfg.device = torch.device("cpu")
+net = mutils.create_model(cfg, use_parallel=False)
+# data-parallel training exchanges ONE buffer: the flat fp32 gradient the engine writes (here filled by hand: the
+# engine itself needs a GPU); every p.grad is a view of it, so the optimiser sees the averaged gradient
+n = sum(p.numel() for p in net.parameters())
+net._flat_grad = torch.full((n,), float(rank + 1))
+view = net._flat_grad[:10]
+net.allreduce_grads()
+assert torch.allclose(net._flat_grad, torch.full((n,), (1 + world) / 2.0)), net._flat_grad[:4]
+assert view.data_ptr() == net._flat_grad.data_ptr() and float(view[0]) == (1 + world) / 2.0
+print("TRAIN_RANK_OK", rank)
+dist.destroy_process_group()
+''' % (ROOT, ROOT)
+
+
+def test_world_size_2_gradient_allreduce(tmp_path):
+    script = os.path.join(tmp_path, "child_train.py")
+    open(script, "w").write(GLOO_TRAIN_CHILD)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534", script],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("TRAIN_RANK_OK") == 2
