@@ -140,9 +140,10 @@ int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma,
 int mdb_conv3d_backward(const void* dy, const void* x, const float* w, int batch, int cin, int cout, int z, int y_,
                         int x_, int ksize, int stride, float* dw, void* dx, void* stream);
 /* Backward of mdb_groupnorm_act (bf16): da = dL/dy [B][V][C] -> dx [B][V][C], dgamma / dbeta fp32 [C]. `add`
- * (nullable, [B][V][C]) is summed into dx. Dropout (p, seed) as in mdb_unet_set_dropout. Synchronises. */
+ * (nullable, [B][V][C]) is summed into dx. Dropout (p, seed) as in mdb_unet_set_dropout. `da` is used as scratch
+ * (overwritten with the pre-activation gradient). Synchronises. */
 int mdb_groupnorm_act_backward(const void* x, const long long* stats, const float* gamma, const float* beta,
-                               const void* da, const void* add, void* dx, float* dgamma, float* dbeta, int batch,
+                               void* da, const void* add, void* dx, float* dgamma, float* dbeta, int batch,
                                long long voxels, int channels, int silu, float dropout_p, unsigned long long seed,
                                void* stream);
 

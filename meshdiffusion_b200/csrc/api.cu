@@ -287,7 +287,7 @@ int mdb_conv3d_backward(const void* dy, const void* x, const float* w, int B, in
   MDB_API_END
 }
 
-int mdb_groupnorm_act_backward(const void* x, const long long* stats, const float* gamma, const float* beta, const void* da,
+int mdb_groupnorm_act_backward(const void* x, const long long* stats, const float* gamma, const float* beta, void* da,
                                const void* add, void* dx, float* dgamma, float* dbeta, int B, long long V, int C, int silu,
                                float dropout_p, unsigned long long seed, void* stream) {
   MDB_API_BEGIN

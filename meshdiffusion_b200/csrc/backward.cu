@@ -43,32 +43,15 @@ static inline int blocks_x(long long voxels, int k, int B) {
   return gx < 1 ? 1 : (int)gx;
 }
 
-// ---- GroupNorm backward. A thread owns GV = 4 consecutive channels (8-byte vectors): half the per-thread state of a
-// 16-byte layout, so 4 blocks of 256 threads fit per SM and, with 4 voxels unrolled, ~64 KB of loads are in flight
-// per SM -- what an HBM-bound kernel needs (measured: the 16-byte / 2-blocks-per-SM version reached 1.4 TB/s).
-constexpr int GV = 4;
-
-__device__ __forceinline__ void unpack4(const uint2& raw, float* x) {
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
-}
-__device__ __forceinline__ uint2 pack4(const float* x) {
-  uint2 t;
-  *reinterpret_cast<__nv_bfloat162*>(&t.x) = __floats2bfloat162_rn(x[0], x[1]);
-  *reinterpret_cast<__nv_bfloat162*>(&t.y) = __floats2bfloat162_rn(x[2], x[3]);
-  return t;
-}
-
-// per-channel constants of the thread's GV channels: xhat = x*rs + nm, y = x*ysc + ysh
-__device__ __forceinline__ void gn_consts(const GnBwdArgs& a, int b, int c, float* rs, float* nm, float* ysc, float* ysh) {
+// mean / rstd of the GroupNorm group of each of the thread's VEC channels, from the forward statistics
+__device__ __forceinline__ void gn_stats_of(const GnBwdArgs& a, int b, int c, float* mean, float* rstd) {
   const int C = a.C0 + a.C1;
   const int cpg = C / a.groups;
   const double n = (double)a.voxels * cpg;
   int cur_g = -1;
   float m = 0.f, r = 0.f;
 #pragma unroll
-  for (int j = 0; j < GV; ++j) {
+  for (int j = 0; j < VEC; ++j) {
     const int g = (c + j) / cpg;
     if (g != cur_g) {
       cur_g = g;
@@ -84,74 +67,76 @@ __device__ __forceinline__ void gn_consts(const GnBwdArgs& a, int b, int c, floa
       m = (float)mm;
       r = (float)(1.0 / sqrt(var + (double)a.eps));
     }
-    const float gm = a.gamma[c + j];
-    rs[j] = r; nm[j] = -m * r;
-    ysc[j] = r * gm; ysh[j] = fmaf(-m * r, gm, a.beta[c + j]);
+    mean[j] = m; rstd[j] = r;
   }
 }
 
-// dy[j] = da[j] * dropout * act'(y[j]); xh[j] = normalised input
-__device__ __forceinline__ void gn_dy4(const GnBwdArgs& a, const float* x, const float* da, const float* rs, const float* nm,
-                                       const float* ysc, const float* ysh, long long e0, float* xh, float* dy) {
-  unsigned long long h = 0;
-  if (a.drop_thresh > 0) h = drop_hash64(a.seed, (unsigned long long)(e0 >> 2));
+// dy[j] = da[j] * act'(y[j]) * dropout, xh[j] = normalised input
+__device__ __forceinline__ void gn_dy(const GnBwdArgs& a, const float* x, const float* da, const float* mean, const float* rstd,
+                                      const float* g, const float* be, long long e0, float* xh, float* dy) {
+  unsigned long long h0 = 0, h1 = 0;
+  if (a.drop_thresh > 0) { h0 = drop_hash64(a.seed, (unsigned long long)(e0 >> 2)); h1 = drop_hash64(a.seed, (unsigned long long)(e0 >> 2) + 1); }
 #pragma unroll
-  for (int j = 0; j < GV; ++j) {
-    xh[j] = fmaf(x[j], rs[j], nm[j]);
+  for (int j = 0; j < VEC; ++j) {
+    xh[j] = (x[j] - mean[j]) * rstd[j];
     float d = da[j];
     if (a.drop_thresh > 0) {
-      const unsigned r16 = (unsigned)((h >> (16 * j)) & 0xFFFFu);
+      const unsigned r16 = (unsigned)(((j < 4 ? h0 : h1) >> (16 * (j & 3))) & 0xFFFFu);
       d = r16 >= (unsigned)a.drop_thresh ? d * a.drop_scale : 0.f;
     }
-    if (a.silu) d *= dsilu(fmaf(x[j], ysc[j], ysh[j]));
+    if (a.silu) d *= dsilu(fmaf(g[j], xh[j], be[j]));
     dy[j] = d;
   }
 }
 
-__global__ void __launch_bounds__(256, 4) gn_bwd_reduce_kernel(GnBwdArgs a, int cv, int k) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(GnBwdArgs a, int cv, int k) {
   constexpr int UNROLL = 4;
-  __shared__ float red[256 * GV * 2];
+  __shared__ float red[256 * VEC * 2];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
   const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
-  const int c = cvi * GV;
-  float rs[GV], nm[GV], ysc[GV], ysh[GV];
-  gn_consts(a, b, c, rs, nm, ysc, ysh);
+  const int c = cvi * VEC;
+  float mean[VEC], rstd[VEC], g[VEC], be[VEC];
+  gn_stats_of(a, b, c, mean, rstd);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { g[j] = a.gamma[c + j]; be[j] = a.beta[c + j]; }
   const bool first = c < a.C0;
   const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 + c) * 2
                           : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 + (c - a.C0)) * 2;
   const long long src_stride = (first ? a.ld0 : a.ld1) * 2;
   const char* dsrc = (const char*)a.da + ((long long)b * a.voxels * C + c) * 2;
   const long long d_stride = (long long)C * 2;
-  float s1[GV], s2[GV];
+  float s1[VEC], s2[VEC];
 #pragma unroll
-  for (int j = 0; j < GV; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const long long step = (long long)gridDim.x * k;
   for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
-    uint2 rx[UNROLL], rd[UNROLL];
+    uint4 rx[UNROLL], rd[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
-      if (v < a.voxels) { rx[u] = __ldg((const uint2*)(src + v * src_stride)); rd[u] = __ldg((const uint2*)(dsrc + v * d_stride)); }
+      if (v < a.voxels) { rx[u] = __ldg((const uint4*)(src + v * src_stride)); rd[u] = __ldg((const uint4*)(dsrc + v * d_stride)); }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
       if (v >= a.voxels) continue;
-      float x[GV], da[GV], xh[GV], dy[GV];
-      unpack4(rx[u], x); unpack4(rd[u], da);
-      gn_dy4(a, x, da, rs, nm, ysc, ysh, ((long long)b * a.voxels + v) * C + c, xh, dy);
+      float x[VEC], da[VEC], xh[VEC], dy[VEC];
+      unpack8(rx[u], x); unpack8(rd[u], da);
+      gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
 #pragma unroll
-      for (int j = 0; j < GV; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], xh[j], s2[j]); }
+      for (int j = 0; j < VEC; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], xh[j], s2[j]); }
+      // dy replaces da in place: pass 2 then needs neither the activation derivative nor the dropout hash again
+      *((uint4*)(const_cast<char*>(dsrc) + v * d_stride)) = pack8(dy);
     }
   }
 #pragma unroll
-  for (int j = 0; j < GV; ++j) { red[(threadIdx.x * GV + j) * 2] = s1[j]; red[(threadIdx.x * GV + j) * 2 + 1] = s2[j]; }
+  for (int j = 0; j < VEC; ++j) { red[(threadIdx.x * VEC + j) * 2] = s1[j]; red[(threadIdx.x * VEC + j) * 2 + 1] = s2[j]; }
   __syncthreads();
   if (vl == 0) {
-    for (int j = 0; j < GV; ++j) {
+    for (int j = 0; j < VEC; ++j) {
       float t1 = 0.f, t2 = 0.f;
-      for (int l = 0; l < k; ++l) { t1 += red[((l * cv + cvi) * GV + j) * 2]; t2 += red[((l * cv + cvi) * GV + j) * 2 + 1]; }
+      for (int l = 0; l < k; ++l) { t1 += red[((l * cv + cvi) * VEC + j) * 2]; t2 += red[((l * cv + cvi) * VEC + j) * 2 + 1]; }
       float* o = a.part + (((long long)blockIdx.x * gridDim.y + b) * C + c + j) * 2;
       o[0] = t1; o[1] = t2;
     }
@@ -176,8 +161,8 @@ __global__ void gn_bwd_param_kernel(const float* __restrict__ sums, float* dgamm
 
 static void gn_launch_shape(const GnBwdArgs& a, int& cv, int& k) {
   const int C = a.C0 + a.C1;
-  cv = C / GV;
-  if (cv < 1 || cv > 256 || C % GV != 0 || a.C0 % GV != 0) throw std::runtime_error("mdb: unsupported channel count in GroupNorm backward");
+  cv = C / VEC;
+  if (cv < 1 || cv > 256 || C % VEC != 0 || a.C0 % VEC != 0) throw std::runtime_error("mdb: unsupported channel count in GroupNorm backward");
   k = 256 / cv;
 }
 
@@ -194,23 +179,24 @@ void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s) {
   MDB_LAUNCH_CHECK();
 }
 
-__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
   constexpr int UNROLL = 2;
-  __shared__ float red[256 * GV];
+  __shared__ float red[256 * VEC];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
   const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
-  const int c = cvi * GV;
-  float rs[GV], nm[GV], ysc[GV], ysh[GV], m1[GV], m2[GV];
-  gn_consts(a, b, c, rs, nm, ysc, ysh);
+  const int c = cvi * VEC;
+  // dx = c1*dy - m1 - xhat*m2 (+ addends), xhat = x*rs + nm; `da` holds dy (written by pass 1)
+  float rs[VEC], nm[VEC], c1[VEC], m1[VEC], m2[VEC];
   {
-    // dx = rstd*(gamma*dy - A/n - xhat*Bq/n), A = sum_group gamma*S1, Bq = sum_group gamma*S2 (rstd*gamma == ysc)
+    float mean[VEC], rstd[VEC];
+    gn_stats_of(a, b, c, mean, rstd);
     const int cpg = C / a.groups;
     const float inv_n = 1.f / ((float)a.voxels * (float)cpg);
     int cur_g = -1;
     float A = 0.f, Bq = 0.f;
 #pragma unroll
-    for (int j = 0; j < GV; ++j) {
+    for (int j = 0; j < VEC; ++j) {
       const int gidx = (c + j) / cpg;
       if (gidx != cur_g) {
         cur_g = gidx;
@@ -222,8 +208,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
           Bq = fmaf(gm, a.sums[((long long)b * C + cc) * 2 + 1], Bq);
         }
       }
-      m1[j] = rs[j] * A * inv_n;
-      m2[j] = rs[j] * Bq * inv_n;
+      rs[j] = rstd[j]; nm[j] = -mean[j] * rstd[j];
+      c1[j] = rstd[j] * a.gamma[c + j];
+      m1[j] = rstd[j] * A * inv_n;
+      m2[j] = rstd[j] * Bq * inv_n;
     }
   }
   const bool first = c < a.C0;
@@ -235,46 +223,46 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
   char* dst = (char*)a.dx + ((long long)b * a.voxels * C + c) * 2;
   const char* p0 = a.add0 ? (const char*)a.add0 + ((long long)b * a.voxels * a.add0_ld + c) * 2 : nullptr;
   const char* p1 = a.add1 ? (const char*)a.add1 + ((long long)b * a.voxels * a.add1_ld + c) * 2 : nullptr;
-  float cs[GV];
+  float cs[VEC];
 #pragma unroll
-  for (int j = 0; j < GV; ++j) cs[j] = 0.f;
+  for (int j = 0; j < VEC; ++j) cs[j] = 0.f;
   const long long step = (long long)gridDim.x * k;
   for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
-    uint2 rx[UNROLL], rd[UNROLL], r0[UNROLL], r1[UNROLL];
+    uint4 rx[UNROLL], rd[UNROLL], r0[UNROLL], r1[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
-      r0[u] = make_uint2(0, 0); r1[u] = make_uint2(0, 0);
+      r0[u] = make_uint4(0, 0, 0, 0); r1[u] = make_uint4(0, 0, 0, 0);
       if (v < a.voxels) {
-        rx[u] = __ldg((const uint2*)(src + v * src_stride));
-        rd[u] = __ldg((const uint2*)(dsrc + v * d_stride));
-        if (p0) r0[u] = __ldg((const uint2*)(p0 + v * a.add0_ld * 2));
-        if (p1) r1[u] = __ldg((const uint2*)(p1 + v * a.add1_ld * 2));
+        rx[u] = __ldg((const uint4*)(src + v * src_stride));
+        rd[u] = *((const uint4*)(dsrc + v * d_stride));  // written by pass 1 of this very step: no read-only path
+        if (p0) r0[u] = __ldg((const uint4*)(p0 + v * a.add0_ld * 2));
+        if (p1) r1[u] = __ldg((const uint4*)(p1 + v * a.add1_ld * 2));
       }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
       if (v >= a.voxels) continue;
-      float x[GV], da[GV], xh[GV], dy[GV], e0[GV], e1[GV], o[GV];
-      unpack4(rx[u], x); unpack4(rd[u], da); unpack4(r0[u], e0); unpack4(r1[u], e1);
-      gn_dy4(a, x, da, rs, nm, ysc, ysh, ((long long)b * a.voxels + v) * C + c, xh, dy);
+      float x[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
+      unpack8(rx[u], x); unpack8(rd[u], dy); unpack8(r0[u], e0); unpack8(r1[u], e1);
 #pragma unroll
-      for (int j = 0; j < GV; ++j) {
-        o[j] = fmaf(ysc[j], dy[j], -m1[j]) - xh[j] * m2[j] + e0[j] + e1[j];
+      for (int j = 0; j < VEC; ++j) {
+        const float xh = fmaf(x[j], rs[j], nm[j]);
+        o[j] = fmaf(c1[j], dy[j], -m1[j]) - xh * m2[j] + e0[j] + e1[j];
         cs[j] += o[j];
       }
-      *((uint2*)(dst + v * d_stride)) = pack4(o);
+      *((uint4*)(dst + v * d_stride)) = pack8(o);
     }
   }
   if (a.cs_part) {  // per-(sample, channel) column sums of dx for the bias / time-embedding gradients downstream
 #pragma unroll
-    for (int j = 0; j < GV; ++j) red[threadIdx.x * GV + j] = cs[j];
+    for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = cs[j];
     __syncthreads();
     if (vl == 0) {
-      for (int j = 0; j < GV; ++j) {
+      for (int j = 0; j < VEC; ++j) {
         float t = 0.f;
-        for (int l = 0; l < k; ++l) t += red[(l * cv + cvi) * GV + j];
+        for (int l = 0; l < k; ++l) t += red[(l * cv + cvi) * VEC + j];
         a.cs_part[((long long)blockIdx.x * gridDim.y + b) * C + c + j] = t;
       }
     }

@@ -19,12 +19,13 @@ inline int kBwdPartRows(int B) { return kBwdTargetBlocks + B; }
 //   forward:  y = gamma*xhat + beta, a = drop(act(y));   given da = dL/da  [B][V][C] dense
 //   pass 1 (reduce): S1[b][c] = sum_v dy, S2[b][c] = sum_v dy*xhat           (dy = da * act'(y) * drop)
 //   pass 2 (apply):  dx = rstd*(gamma*dy - mean_g(gamma*dy) - xhat*mean_g(gamma*dy*xhat)) + add0 + add1
+//   Pass 1 stores dy over da, so the activation derivative and the dropout hash are evaluated once per element.
 struct GnBwdArgs {
   const void* x0; int C0; long long ld0;   // forward input (raw), first source
   const void* x1; int C1; long long ld1;   // second (concatenated) source or null
   const long long* stats0; const long long* stats1;  // forward statistics of the sources ([B][Ci][2] fixed point)
   const float* gamma; const float* beta;
-  const void* da;          // [B][V][C] dense, activation dtype
+  const void* da;          // [B][V][C] dense, activation dtype; OVERWRITTEN with dy by pass 1 (pass 2 reads dy from it)
   long long voxels; int silu; int groups; float eps;
   // dropout that followed the activation in the forward pass (keep iff hash16(seed, element) >= drop_thresh)
   int drop_thresh; float drop_scale; unsigned long long seed;

@@ -96,6 +96,7 @@ def groupnorm_act_backward(x, stats, gamma, beta, da, add=None, silu=True, dropo
     dx = torch.empty_like(x)
     dg = torch.empty(C, device=x.device, dtype=torch.float32)
     db = torch.empty(C, device=x.device, dtype=torch.float32)
+    da = da.clone()  # the kernel pair overwrites dL/dy with the pre-activation gradient
     _native.check(L.mdb_groupnorm_act_backward(_native.ptr(x), _native.ptr(stats), _native.ptr(g), _native.ptr(bt), _native.ptr(da),
                                                _native.ptr(add), _native.ptr(dx), _native.ptr(dg), _native.ptr(db), B, V, C,
                                                1 if silu else 0, float(dropout_p), int(seed), _native.current_stream()))
