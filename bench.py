@@ -93,6 +93,7 @@ def build_model(precision, batch, device):
     torch.manual_seed(0)
     model = mutils.create_model(cfg)
     random_init_nondegenerate(model.module)
+    model.eval()
     return cfg, model
 
 

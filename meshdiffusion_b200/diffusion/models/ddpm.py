@@ -349,7 +349,9 @@ class ScoreNet(nn.Module):
         x = x.float().contiguous()
         labels = labels.to(device=x.device, dtype=torch.float32).contiguous()
         B = x.shape[0]
-        if torch.is_grad_enabled() and any(self._param(n).requires_grad for n in self._trainable):
+        # training path: model.train() + autograd enabled (what step_fn(train=True) sets up, losses.py:104-139 with
+        # get_model_fn(train=True)); everything else -- model.eval() or no_grad -- is the inference engine
+        if self.training and torch.is_grad_enabled() and any(self._param(n).requires_grad for n in self._trainable):
             out = _ScoreNetFn.apply(self, x, labels, *[self._param(n) for n in self._trainable])
             if self.scale_by_sigma:
                 out = out / self.sigmas.to(out.device)[labels.long(), None, None, None, None].float()

@@ -36,6 +36,7 @@ def build_model(cfg, device, state_seed):
     net = model.module
     sd = synth.synthetic_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()}, seed=state_seed)
     net.load_state_dict(sd)
+    model.eval()  # inference engine; the training tests switch to .train() explicitly
     return model, sd
 
 
