@@ -298,3 +298,43 @@ def test_unet_backward_matches_reference_golden(name):
         assert np.abs(got[1:] - sig[1:]).max() < tol, f"{n}: projections {got[1:]} vs {sig[1:]}"
         worst = max(worst, np.abs(got[1:] - sig[1:]).max() / tot)
     print(f"{name}: {len(gold['names'])} tensors, worst projection error / |g| {worst:.3e}")
+
+
+def test_res64_full_backward_vs_autograd():
+    """Full-size network (64^3 ... 4^3 levels, CTA-pair data gradients, 16-way split weight gradients, both attention
+    resolutions): every gradient tensor against fp32 autograd through the oracle, B = 1."""
+    from helpers import ddpm_loss, full_config
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = full_config("res64", "bf16")
+    cfg.model.dropout = 0.0
+    model, sd = build_model(cfg, "cuda:0", 5)
+    net = model.module
+    net.train()
+    R = 64
+    x, labels = synth.synthetic_inputs(R, 1, 6, sd["mask"])
+    x, labels = x.cuda(), labels.cuda()
+    noise = torch.randn(x.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    mask = sd["mask"].cuda().view(1, 1, R, R, R)
+    loss = ddpm_loss(model(x, labels), noise, mask)
+    loss.backward()
+    ours = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    net.release_engine()
+    torch.cuda.empty_cache()
+    osd = {k: (v.cuda().clone().requires_grad_(True) if v.dtype == torch.float32 and k not in ("mask", "coords") else v.cuda()) for k, v in sd.items()}
+    ref_loss = ddpm_loss(unet_oracle.unet_forward(osd, unet_oracle.arch_from_config(cfg), x, labels), noise, mask)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 3e-2 * abs(ref_loss.item())
+    tot_num = tot_den = 0.0
+    rows = []
+    for n, g in ours.items():
+        if n not in osd or osd[n].grad is None:
+            continue
+        num = (g - osd[n].grad).double().pow(2).sum().item()
+        den = osd[n].grad.double().pow(2).sum().item()
+        tot_num += num; tot_den += den
+        rows.append((n, num, den))
+    glob = (tot_num / tot_den) ** 0.5
+    worst = max(((n, (num / den) ** 0.5) for n, num, den in rows if den > 1e-8 * tot_den), key=lambda t: t[1])
+    print(f"res64 full: loss {loss.item():.5f} vs {ref_loss.item():.5f}; {len(rows)} tensors, global rel-l2 {glob:.3e}, worst {worst[0]} {worst[1]:.3e}")
+    assert glob < 4e-2 and worst[1] < 1.5e-1
