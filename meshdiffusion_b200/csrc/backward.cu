@@ -89,6 +89,8 @@ __device__ __forceinline__ void gn_dy(const GnBwdArgs& a, const float* x, const 
   }
 }
 
+// Pass 1. Per element: h = 0.5*y straight from x (one FMA with folded constants), silu'(y) = t + 0.5*h*q with
+// t = (1+tanh h)/2, q = 1 - tanh^2 h; S2 is accumulated as sum(dy*x) and rebased to sum(dy*xhat) once per thread.
 __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(GnBwdArgs a, int cv, int k) {
   constexpr int UNROLL = 4;
   __shared__ float red[256 * VEC * 2];
@@ -96,15 +98,22 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(GnBwdArgs a, int 
   const int b = blockIdx.y;
   const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
   const int c = cvi * VEC;
-  float mean[VEC], rstd[VEC], g[VEC], be[VEC];
-  gn_stats_of(a, b, c, mean, rstd);
+  float hsc[VEC], hsh[VEC];
+  {
+    float mean[VEC], rstd[VEC];
+    gn_stats_of(a, b, c, mean, rstd);
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { g[j] = a.gamma[c + j]; be[j] = a.beta[c + j]; }
+    for (int j = 0; j < VEC; ++j) {
+      const float sc = rstd[j] * a.gamma[c + j];
+      hsc[j] = 0.5f * sc;
+      hsh[j] = 0.5f * fmaf(-mean[j], sc, a.beta[c + j]);
+    }
+  }
   const bool first = c < a.C0;
   const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 + c) * 2
                           : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 + (c - a.C0)) * 2;
   const long long src_stride = (first ? a.ld0 : a.ld1) * 2;
-  const char* dsrc = (const char*)a.da + ((long long)b * a.voxels * C + c) * 2;
+  char* dsrc = const_cast<char*>((const char*)a.da) + ((long long)b * a.voxels * C + c) * 2;
   const long long d_stride = (long long)C * 2;
   float s1[VEC], s2[VEC];
 #pragma unroll
@@ -115,20 +124,46 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(GnBwdArgs a, int 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
-      if (v < a.voxels) { rx[u] = __ldg((const uint4*)(src + v * src_stride)); rd[u] = __ldg((const uint4*)(dsrc + v * d_stride)); }
+      if (v < a.voxels) { rx[u] = __ldg((const uint4*)(src + v * src_stride)); rd[u] = *((const uint4*)(dsrc + v * d_stride)); }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
       if (v >= a.voxels) continue;
-      float x[VEC], da[VEC], xh[VEC], dy[VEC];
-      unpack8(rx[u], x); unpack8(rd[u], da);
-      gn_dy(a, x, da, mean, rstd, g, be, ((long long)b * a.voxels + v) * C + c, xh, dy);
+      float x[VEC], dy[VEC];
+      unpack8(rx[u], x); unpack8(rd[u], dy);
+      if (a.drop_thresh > 0) {
+        const unsigned long long e4 = (unsigned long long)((((long long)b * a.voxels + v) * C + c) >> 2);
+        const unsigned long long h0 = drop_hash64(a.seed, e4), h1 = drop_hash64(a.seed, e4 + 1);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], xh[j], s2[j]); }
+        for (int j = 0; j < VEC; ++j) {
+          const unsigned r16 = (unsigned)(((j < 4 ? h0 : h1) >> (16 * (j & 3))) & 0xFFFFu);
+          dy[j] = r16 >= (unsigned)a.drop_thresh ? dy[j] * a.drop_scale : 0.f;
+        }
+      }
+      if (a.silu) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float h = fmaf(x[j], hsc[j], hsh[j]);
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+          const float q = fmaf(-th, th, 1.f);
+          const float t = fmaf(0.5f, th, 0.5f);
+          dy[j] *= fmaf(0.5f, h * q, t);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s1[j] += dy[j]; s2[j] = fmaf(dy[j], x[j], s2[j]); }
       // dy replaces da in place: pass 2 then needs neither the activation derivative nor the dropout hash again
-      *((uint4*)(const_cast<char*>(dsrc) + v * d_stride)) = pack8(dy);
+      *((uint4*)(dsrc + v * d_stride)) = pack8(dy);
     }
+  }
+  {
+    // sum(dy*xhat) = rstd*sum(dy*x) - mean*rstd*sum(dy)
+    float mean[VEC], rstd[VEC];
+    gn_stats_of(a, b, c, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s2[j] = rstd[j] * (s2[j] - mean[j] * s1[j]);
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { red[(threadIdx.x * VEC + j) * 2] = s1[j]; red[(threadIdx.x * VEC + j) * 2 + 1] = s2[j]; }
@@ -186,8 +221,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int c
   const int b = blockIdx.y;
   const int cvi = threadIdx.x % cv, vl = threadIdx.x / cv;
   const int c = cvi * VEC;
-  // dx = c1*dy - m1 - xhat*m2 (+ addends), xhat = x*rs + nm; `da` holds dy (written by pass 1)
-  float rs[VEC], nm[VEC], c1[VEC], m1[VEC], m2[VEC];
+  // dx = c1*dy - m1 - xhat*m2 (+ addends) with xhat = (x - mean)*rstd, folded to c1*dy - k0 - x*k1; `da` holds dy
+  float c1[VEC], k0[VEC], k1[VEC];
   {
     float mean[VEC], rstd[VEC];
     gn_stats_of(a, b, c, mean, rstd);
@@ -208,10 +243,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int c
           Bq = fmaf(gm, a.sums[((long long)b * C + cc) * 2 + 1], Bq);
         }
       }
-      rs[j] = rstd[j]; nm[j] = -mean[j] * rstd[j];
+      const float m1 = rstd[j] * A * inv_n, m2 = rstd[j] * Bq * inv_n;
       c1[j] = rstd[j] * a.gamma[c + j];
-      m1[j] = rstd[j] * A * inv_n;
-      m2[j] = rstd[j] * Bq * inv_n;
+      k1[j] = rstd[j] * m2;
+      k0[j] = m1 - mean[j] * rstd[j] * m2;
     }
   }
   const bool first = c < a.C0;
@@ -248,8 +283,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int c
       unpack8(rx[u], x); unpack8(rd[u], dy); unpack8(r0[u], e0); unpack8(r1[u], e1);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const float xh = fmaf(x[j], rs[j], nm[j]);
-        o[j] = fmaf(c1[j], dy[j], -m1[j]) - xh * m2[j] + e0[j] + e1[j];
+        o[j] = fmaf(-x[j], k1[j], fmaf(c1[j], dy[j], -k0[j])) + e0[j] + e1[j];
         cs[j] += o[j];
       }
       *((uint4*)(dst + v * d_stride)) = pack8(o);
