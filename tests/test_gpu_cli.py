@@ -54,3 +54,20 @@ def test_cond_gen_cli_and_mesh_extraction(tmp_path):
         assert faces_b.shape[1] == 3 and faces_b.dtype == torch.int64
         if faces_b.numel():
             assert int(faces_b.max()) < verts_b.shape[0]
+
+
+def test_train_cli_writes_reference_checkpoint_layout(tmp_path):
+    """`--mode=train` (BASELINE config 3 plumbing): three optimiser steps on synthetic grids through the engine's
+    forward + backward, then the checkpoint the reference's restore_checkpoint expects (utils.py:23-30)."""
+    wd = os.path.join(tmp_path, "run")
+    r = _run([f"--config={ROOT}/configs/res64.py", "--mode=train", f"--config.training.train_dir={wd}",
+              "--config.data.synthetic=True", "--config.training.batch_size=1", "--config.training.n_iters=3",
+              "--config.training.log_freq=1", "--config.training.snapshot_freq_for_preemption=2",
+              "--config.training.snapshot_freq=100000"], cwd=str(tmp_path))
+    ck = torch.load(os.path.join(wd, "checkpoints-meta", "checkpoint.pth"), map_location="cpu", weights_only=False)
+    assert set(ck.keys()) == {"optimizer", "model", "ema", "step"}
+    assert ck["step"] >= 2
+    assert all(k.startswith("module.") for k in ck["model"])
+    assert len(ck["ema"]["shadow_params"]) == 494
+    losses = [float(l.split("training_loss:")[1]) for l in (r.stderr + r.stdout).splitlines() if "training_loss:" in l]
+    assert len(losses) >= 3 and all(np.isfinite(losses))
