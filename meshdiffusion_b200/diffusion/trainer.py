@@ -39,6 +39,11 @@ def synthetic_grids(batch, resolution, device, generator=None):
     return x
 
 
+def _path_or_none(p):
+    """The stock configs carry the literal "PLACEHOLDER" for unset paths (configs/res64.py): no filter list then."""
+    return None if p in (None, "", "PLACEHOLDER") else p
+
+
 def _init_distributed(device):
     """(rank, world): joins the NCCL group when launched under torchrun, else (0, 1)."""
     import torch.distributed as dist
@@ -84,16 +89,40 @@ def train(config):
     train_step_fn = losses.get_step_fn(sde, train=True, optimize_fn=optimize_fn, mask=mask,
                                        loss_type=config.training.loss_type)
 
-    if not config.data.get("synthetic", False):
-        raise NotImplementedError("only config.data.synthetic=True grids are wired up (the dataset loader is a 'next' row, "
-                                  "SURVEY section 8f-2)")
+    synthetic = bool(config.data.get("synthetic", False))
+    data_iter = train_loader = sampler = None
+    if not synthetic:
+        # trainer.py:64-75 of the reference: JSON list of per-shape grids, shuffled DataLoader; under torchrun every rank
+        # reads its own shard (DistributedSampler) instead of nn.DataParallel scattering one batch
+        from ..dataset.shapenet_dmtet_dataset import ShapeNetDMTetDataset
+        dataset = ShapeNetDMTetDataset(config.data.meta_path, deform_scale=config.model.get("deform_scale", 1.0), aug=True,
+                                       grid_mask=mask.cpu(), filter_meta_path=_path_or_none(config.data.get("filter_meta_path", None)),
+                                       normalize_sdf=config.data.get("normalize_sdf", True),
+                                       extension=config.data.get("extension", "pt"))
+        if world > 1:
+            sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True)
+        train_loader = torch.utils.data.DataLoader(dataset, batch_size=config.training.batch_size, shuffle=sampler is None,
+                                                   sampler=sampler, num_workers=config.data.get("num_workers", 0), pin_memory=True)
+        data_iter = iter(train_loader)
+
+    def next_batch(gen):
+        nonlocal data_iter
+        if synthetic:
+            return synthetic_grids(config.training.batch_size, R, device, gen) * mask
+        try:
+            batch = next(data_iter)
+        except StopIteration:
+            data_iter = iter(train_loader)
+            batch = next(data_iter)
+        return batch.to(device, non_blocking=True)
+
     iter_size = config.training.iter_size
     gen = torch.Generator(device=device).manual_seed(int(config.get("seed", 42)) + int(os.environ.get("RANK", "0")))
     logging.info("Starting training loop at step %d.", initial_step // iter_size)
     for step in range(initial_step // iter_size, config.training.n_iters):
         tmp_loss = 0.0
         for inner in range(iter_size):
-            batch = synthetic_grids(config.training.batch_size, R, device, gen) * mask
+            batch = next_batch(gen)
             loss = train_step_fn(state, batch, clear_grad=(inner == 0), update_param=(inner == iter_size - 1))["loss"]
             tmp_loss += loss.item()
         tmp_loss /= iter_size

@@ -172,3 +172,33 @@ def test_world_size_2_gradient_allreduce(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("TRAIN_RANK_OK") == 2
+
+
+def test_dataset_items_match_reference_golden(tmp_path):
+    """ShapeNetDMTetDataset: items bit-identical to the reference class on the committed synthetic shapes (filter list,
+    sign quirk, seeded jitter augmentation, mask multiply, right padding); golden from the reference class itself."""
+    from meshdiffusion_b200.dataset.shapenet_dmtet_dataset import ShapeNetDMTetDataset
+    gold = np.load(os.path.join(GOLD, "dataset_items.npz"))
+    paths = []
+    for i, raw in enumerate(gold["raw"]):
+        p = os.path.join(tmp_path, f"shape_{i}.pt")
+        torch.save(torch.tensor(raw), p)
+        paths.append(p)
+    meta = os.path.join(tmp_path, "meta.json")
+    json.dump(paths, open(meta, "w"))
+    filt = os.path.join(tmp_path, "filter.json")
+    json.dump([int(v) for v in gold["filter"]], open(filt, "w"))
+    mask = torch.tensor(gold["mask"])
+    k = 0
+    for aug in (False, True):
+        ds = ShapeNetDMTetDataset(meta, mask, deform_scale=3.0, aug=aug, filter_meta_path=filt, normalize_sdf=True, extension="pt")
+        assert len(ds) == 3
+        for i in range(3):
+            torch.manual_seed(100 + i)
+            assert np.array_equal(ds[i].numpy(), gold["items"][k]), (aug, i)
+            k += 1
+    # the .npy branch (a NameError in the reference) loads the same values
+    np.save(os.path.join(tmp_path, "shape_9.npy"), gold["raw"][0])
+    json.dump([os.path.join(tmp_path, "shape_9.npy")], open(meta, "w"))
+    ds = ShapeNetDMTetDataset(meta, mask, aug=False, extension="npy")
+    assert np.array_equal(ds[0].numpy(), gold["items"][0])
