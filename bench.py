@@ -82,11 +82,11 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
 
 
-def build_model(precision, batch, device):
-    from configs import res64
+def build_model(precision, batch, device, res=64):
+    from configs import res64, res128
     from meshdiffusion_b200.diffusion.models import utils as mutils
     from meshdiffusion_b200.diffusion.models.init_utils import random_init_nondegenerate
-    cfg = res64.get_config()
+    cfg = (res128 if res == 128 else res64).get_config()
     cfg.model.compute_dtype = precision
     cfg.model.engine_max_batch = batch
     cfg.device = device
@@ -113,8 +113,8 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    B, R, K, W = args.batch, 64, args.steps, args.warmup
-    cfg, model = build_model(args.precision, B, device)
+    B, R, K, W = args.batch, args.res, args.steps, args.warmup
+    cfg, model = build_model(args.precision, B, device, R)
     net = model.module
     sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device=device)
     mask = grid_mask_from_tets(R).to(device)
@@ -210,7 +210,7 @@ def run_ours(args):
                     "algorithmic_flops_per_launch_avg": flops / info["gemm_launches"]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and R == 64:
         cpu = cpu_baseline_port(net, mask, steps=1)
 
     # ---- the same device-resident loop with TF32 operands (the parity-grade mode: 1.5e-3 rel-L2 vs fp32, the class of
@@ -220,7 +220,7 @@ def run_ours(args):
         net.release_engine()
         del model, net
         torch.cuda.empty_cache()
-        cfg2, model2 = build_model("tf32", B, device)
+        cfg2, model2 = build_model("tf32", B, device, R)
         net2 = model2.module
         net2.mask.data[:] = mask.view(1, 1, R, R, R)
         x2 = x.clone()
@@ -241,10 +241,10 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC if R == 64 else METRIC.replace("res-64 (4x64^3)", "res-128 (4x128^3)"), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic (random-init non-degenerate weights, N(0,1)*grid_mask state)",
-            "config": {"workload": "res64.py uncond_gen, batch=32/GPU, PC sampler (ancestral_sampling + none), steps of the N=1000 schedule",
+            "config": {"workload": f"res{R}.py uncond_gen, batch={B}/GPU, PC sampler (ancestral_sampling + none), steps of the N=1000 schedule",
                        "batch_per_gpu": B, "image_size": R, "precision": args.precision,
                        "l2_policy": "inputs larger than L2: per-step activation working set is several GB at batch 32"},
             "samples_per_s": value / N_EVALS_FULL,
@@ -364,13 +364,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="grids per GPU (BASELINE configs[1]: 32)")
+    ap.add_argument("--batch", type=int, default=None, help="grids per GPU (default 32 = BASELINE configs[1]; 8 with --res 128 = configs[3])")
+    ap.add_argument("--res", type=int, default=64, choices=[64, 128], help="64 = the metric's config (default); 128 = BASELINE configs[3] (secondary)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tf32-leg", action="store_true", help="skip the secondary TF32-operand measurement")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event times of one forward as JSON")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 8 if args.res == 128 else 32
     if args.impl == "reference":
         run_reference(args)
         return
