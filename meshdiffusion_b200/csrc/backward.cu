@@ -214,8 +214,7 @@ void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s) {
   MDB_LAUNCH_CHECK();
 }
 
-__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
-  constexpr int UNROLL = 2;
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
   __shared__ float red[256 * VEC];
   const int C = a.C0 + a.C1;
   const int b = blockIdx.y;
@@ -262,32 +261,32 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs a, int c
 #pragma unroll
   for (int j = 0; j < VEC; ++j) cs[j] = 0.f;
   const long long step = (long long)gridDim.x * k;
-  for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
-    uint4 rx[UNROLL], rd[UNROLL], r0[UNROLL], r1[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const long long v = v0 + u * step;
-      r0[u] = make_uint4(0, 0, 0, 0); r1[u] = make_uint4(0, 0, 0, 0);
-      if (v < a.voxels) {
-        rx[u] = __ldg((const uint4*)(src + v * src_stride));
-        rd[u] = *((const uint4*)(dsrc + v * d_stride));  // written by pass 1 of this very step: no read-only path
-        if (p0) r0[u] = __ldg((const uint4*)(p0 + v * a.add0_ld * 2));
-        if (p1) r1[u] = __ldg((const uint4*)(p1 + v * a.add1_ld * 2));
-      }
+  // software pipeline: the loads of voxel i+1 are issued before voxel i is processed, so every warp always has a full
+  // set of requests in flight (the kernel is latency-bound at 2 blocks/SM otherwise: ncu, profiles/r01_ncu_prof_gn_backward.txt)
+  uint4 cx, cd, c0r, c1r;
+  long long v = (long long)blockIdx.x * k + vl;
+  auto issue = [&](long long vv, uint4& qx, uint4& qd, uint4& q0, uint4& q1) {
+    q0 = make_uint4(0, 0, 0, 0); q1 = make_uint4(0, 0, 0, 0);
+    if (vv < a.voxels) {
+      qx = __ldg((const uint4*)(src + vv * src_stride));
+      qd = *((const uint4*)(dsrc + vv * d_stride));  // written by pass 1 of this very step: no read-only path
+      if (p0) q0 = __ldg((const uint4*)(p0 + vv * a.add0_ld * 2));
+      if (p1) q1 = __ldg((const uint4*)(p1 + vv * a.add1_ld * 2));
     }
+  };
+  issue(v, cx, cd, c0r, c1r);
+  for (; v < a.voxels; v += step) {
+    uint4 nx, nd, n0, n1;
+    issue(v + step, nx, nd, n0, n1);
+    float x[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
+    unpack8(cx, x); unpack8(cd, dy); unpack8(c0r, e0); unpack8(c1r, e1);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const long long v = v0 + u * step;
-      if (v >= a.voxels) continue;
-      float x[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
-      unpack8(rx[u], x); unpack8(rd[u], dy); unpack8(r0[u], e0); unpack8(r1[u], e1);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        o[j] = fmaf(-x[j], k1[j], fmaf(c1[j], dy[j], -k0[j])) + e0[j] + e1[j];
-        cs[j] += o[j];
-      }
-      *((uint4*)(dst + v * d_stride)) = pack8(o);
+    for (int j = 0; j < VEC; ++j) {
+      o[j] = fmaf(-x[j], k1[j], fmaf(c1[j], dy[j], -k0[j])) + e0[j] + e1[j];
+      cs[j] += o[j];
     }
+    *((uint4*)(dst + v * d_stride)) = pack8(o);
+    cx = nx; cd = nd; c0r = n0; c1r = n1;
   }
   if (a.cs_part) {  // per-(sample, channel) column sums of dx for the bias / time-embedding gradients downstream
 #pragma unroll
