@@ -35,10 +35,12 @@ __device__ __forceinline__ float dsilu(float y) {
   return s * fmaf(y, 1.f - s, 1.f);
 }
 
-// grid.x for the staged reductions: about kBwdTargetBlocks blocks in total (4 x 148 SMs), whatever the batch
-static inline int blocks_x(long long voxels, int k, int B) {
+// grid.x for the staged, grid-stride kernels: the whole grid is ONE full wave of `target` = 148 x (resident blocks per
+// SM) blocks -- a 608-block launch at 2 blocks/SM (296 resident) spends a third, nearly empty wave on 16 blocks.
+static inline int blocks_x(long long voxels, int k, int B, int target) {
   long long gx = (voxels + (long long)k * 4 - 1) / ((long long)k * 4);
-  const long long want = (kBwdTargetBlocks + B - 1) / B;
+  long long want = target / B;
+  if (want < 1) want = 1;
   if (gx > want) gx = want;
   return gx < 1 ? 1 : (int)gx;
 }
@@ -205,7 +207,7 @@ void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s) {
   int cv, k;
   gn_launch_shape(a, cv, k);
   const int C = a.C0 + a.C1;
-  const int gx = blocks_x(a.voxels, k, B);
+  const int gx = blocks_x(a.voxels, k, B, 296);
   gn_bwd_reduce_kernel<<<dim3(gx, B), cv * k, 0, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
   gn_bwd_sums_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a.part, a.sums, gx, B * C);
@@ -314,13 +316,69 @@ void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s) {
   int cv, k;
   gn_launch_shape(a, cv, k);
   const int C = a.C0 + a.C1;
-  const int gx = blocks_x(a.voxels, k, B);
+  const int gx = blocks_x(a.voxels, k, B, 444);
   gn_bwd_apply_kernel<<<dim3((unsigned)gx, B), cv * k, 0, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
   if (a.cs_part) {
     cs_final_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a.cs_part, a.cs_per, gx, B * C);
     MDB_LAUNCH_CHECK();
   }
+}
+
+// ------------------------------------------------------------------ fused path: constants for the GEMM epilogue, tile reduce
+__global__ void gn_consts_kernel(GnBwdArgs a, float4* __restrict__ out, int B) {
+  const int C = a.C0 + a.C1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const int cpg = C / a.groups, g = c / cpg;
+  long long s1 = 0, s2 = 0;
+  for (int j = 0; j < cpg; ++j) {
+    const int cc = g * cpg + j;
+    const long long* q = (cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * 2 : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * 2;
+    s1 += q[0]; s2 += q[1];
+  }
+  const double n = (double)a.voxels * cpg;
+  const double mm = (double)s1 * (1.0 / 16777216.0) / n;
+  double var = (double)s2 * (1.0 / 16777216.0) / n - mm * mm;
+  if (var < 0) var = 0;
+  const float mean = (float)mm, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+  const float sc = rstd * a.gamma[c];
+  out[i] = make_float4(0.5f * sc, 0.5f * fmaf(-mean, sc, a.beta[c]), rstd, -mean * rstd);
+}
+void launch_gn_consts(const GnBwdArgs& a, float* consts4, int B, cudaStream_t s) {
+  const int C = a.C0 + a.C1;
+  gn_consts_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a, reinterpret_cast<float4*>(consts4), B);
+  MDB_LAUNCH_CHECK();
+}
+
+// grid (ceil(C/32), B), block (32, 8): lane y sums tiles y, y+8, ... in order; the 8 lane sums are added in order
+__global__ void gnb_tile_reduce_kernel(const float* __restrict__ part, float* __restrict__ sums, int T, int bb, int C) {
+  __shared__ float red[8][32][2];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  const long long row0 = (long long)(b / bb) * T;
+  const int sg = b % bb;
+  float t1 = 0.f, t2 = 0.f;
+  if (c < C) {
+    for (int t = threadIdx.y; t < T; t += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(part + (((row0 + t) * bb + sg) * C + c) * 2);
+      t1 += v.x; t2 += v.y;
+    }
+  }
+  red[threadIdx.y][threadIdx.x][0] = t1; red[threadIdx.y][threadIdx.x][1] = t2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    t1 = 0.f; t2 = 0.f;
+    for (int l = 0; l < 8; ++l) { t1 += red[l][threadIdx.x][0]; t2 += red[l][threadIdx.x][1]; }
+    sums[((long long)b * C + c) * 2] = t1; sums[((long long)b * C + c) * 2 + 1] = t2;
+  }
+}
+void launch_gnb_tile_reduce(const GnBwdArgs& a, const float* tile_part, int T, int bb, int B, cudaStream_t s) {
+  const int C = a.C0 + a.C1;
+  gnb_tile_reduce_kernel<<<dim3((C + 31) / 32, B), dim3(32, 8), 0, s>>>(tile_part, a.sums, T, bb, C);
+  MDB_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(a.sums, a.dgamma, a.dbeta, B, C, a.accumulate);
+  MDB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------ column sums (bias / time-embedding gradients)
@@ -388,7 +446,7 @@ void launch_colsum(const ColsumArgs& a, int B, cudaStream_t s) {
   const int cv = a.C / VEC;
   if (cv < 1 || cv > 256 || a.C % VEC != 0) throw std::runtime_error("mdb: unsupported channel count in colsum");
   const int k = 256 / cv;
-  const int gx = blocks_x(a.voxels, k, B);
+  const int gx = blocks_x(a.voxels, k, B, 592);
   colsum_kernel<<<dim3(gx, B), cv * k, 0, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
   colsum_final_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a, gx, B);

@@ -43,6 +43,13 @@ struct GnBwdArgs {
 void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s);  // part -> sums -> dgamma/dbeta
 void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s);
 
+// Fused variant: the data-gradient GEMM that produces `da` applies dy = da*drop*act'(y) in its epilogue (gemm_tc.cuh,
+// GNB) and leaves per-tile column partials; pass 1 above is then replaced by these two small kernels.
+// consts[b][c] = {0.5*rstd*gamma, 0.5*(beta - mean*rstd*gamma), rstd, -mean*rstd}
+void launch_gn_consts(const GnBwdArgs& a, float* consts4, int B, cudaStream_t s);
+// sums[b][c][2] = sum over the T tiles of sample b of part[((b/bb*T + t)*bb + b%bb)][c][2]; then dgamma / dbeta
+void launch_gnb_tile_reduce(const GnBwdArgs& a, const float* tile_part, int T, int bb, int B, cudaStream_t s);
+
 // colsum: per[b][c] = sum_v t[b][v][c]; total[c] (+)= sum_b per[b][c]. `per` (nullable) is written with row pitch
 // per_ld; up to three `total` outputs receive the same values (conv bias + folded shortcut bias, stem biases).
 struct ColsumArgs {

@@ -276,6 +276,21 @@ void GemmOp::set_residual(const void* res, long long ldr, long long batch_stride
   p.res_fp32 = fp32 ? 1 : 0;
 }
 
+void GemmOp::set_gn_backward(const void* x0, long long ld0, int c0, const void* x1, long long ld1, const void* consts, int silu,
+                             float* part) {
+  if (prec != kBF16 || p.out_fp32 || p.ocs != 1) throw std::runtime_error("mdb: the GroupNorm-backward epilogue is built for bf16 NDHWC outputs");
+  if (p.N % 32 != 0 || (x1 && c0 % 32 != 0)) throw std::runtime_error("mdb: GroupNorm-backward epilogue needs 32-channel aligned sources");
+  if (splits > 1) throw std::runtime_error("mdb: GroupNorm-backward epilogue cannot be combined with split-K");
+  gnb = true;
+  p.res = x0; p.res_fp32 = 0; p.batch_fastest = 0;
+  p.rsx = ld0; p.rsy = ld0 * p.X; p.rsz = ld0 * p.X * p.Y; p.rsb = ld0 * p.X * p.Y * p.Z;
+  p.res1 = x1; p.res_c0 = x1 ? c0 : p.N;
+  p.r1sx = ld1; p.r1sy = ld1 * p.X; p.r1sz = ld1 * p.X * p.Y; p.r1sb = ld1 * p.X * p.Y * p.Z;
+  p.gnb_c = reinterpret_cast<const float4*>(consts);
+  p.gnb_silu = silu;
+  p.gnb_part = part;
+}
+
 void GemmOp::encode_bmap(void* ptr, int K, int N, int batch, long long rsb, long long bsb) {
   uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)batch};
   uint64_t strides[2] = {(uint64_t)rsb, (uint64_t)bsb};
@@ -406,10 +421,10 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
-template <int BN, bool TF32, bool CG2>
+template <int BN, bool TF32, bool CG2, bool GNB = false>
 static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, TF32, CG2>;
+  auto kern = gemm_tc_kernel<BN, TF32, CG2, GNB>;
   constexpr int smem = GemmCfg<BN, CG2>::kSmemBytes;
   if (!configured) {
     MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -442,6 +457,20 @@ void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
   if (out_override) p.out = out_override;
   const int tiles_m = p.tx * p.ty * p.tz * p.tb;
   const bool tf = prec == kTF32;
+  if (gnb) {
+    if (tf || p.splits > 1) throw std::runtime_error("mdb: GroupNorm-backward epilogue: bf16, no split-K");
+    p.gnb_drop_thresh = rt_drop_thresh; p.gnb_drop_scale = rt_drop_scale; p.gnb_seed = rt_seed;
+    if (pair) {
+      const int work = ((tiles_m + 1) / 2) * p.n_tiles_n;
+      const int pairs = sm_count() / 2;
+      launch_impl<128, false, true, true>(p, 2 * (work < pairs ? work : pairs), stream);
+    } else {
+      const int total = tiles_m * p.n_tiles_n;
+      const int grid = total < sm_count() ? total : sm_count();
+      if (block_n == 32) launch_impl<32, false, false, true>(p, grid, stream); else launch_impl<128, false, false, true>(p, grid, stream);
+    }
+    return;
+  }
   if (pair) {
     const int work = ((tiles_m + 1) / 2) * p.n_tiles_n;
     const int pairs = sm_count() / 2;

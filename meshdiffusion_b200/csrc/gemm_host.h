@@ -102,6 +102,16 @@ class GemmOp {
   void set_out_col_stride(long long ocs) { p.ocs = ocs; }
   void set_residual(const void* res, long long ldr, long long batch_stride, bool fp32);
   void set_stats(long long* stats) { p.stats = stats; }
+  // GroupNorm-backward epilogue (training data gradients, bf16): the GEMM result is dL/da of a GroupNorm(+SiLU)(+dropout)
+  // whose INPUT is the channel concatenation of x0 (c0 channels, row pitch ld0) and x1; `consts` = [B][N] float4 from
+  // launch_gn_consts; `part` = [gnb_rows()][N][2] per-tile partials for launch_gnb_tile_reduce. Dropout of the layer is
+  // supplied per launch through rt_drop_*.
+  void set_gn_backward(const void* x0, long long ld0, int c0, const void* x1, long long ld1, const void* consts, int silu, float* part);
+  long long gnb_rows() const { return 1LL * p.tx * p.ty * p.tz * p.tb * p.bb; }
+  int gnb_tiles_per_batch_tile() const { return p.tx * p.ty * p.tz; }
+  int gnb_bb() const { return p.bb; }
+  bool gnb = false;
+  int rt_drop_thresh = 0; float rt_drop_scale = 1.f; unsigned long long rt_seed = 0;
   void set_alpha(float a) { p.alpha = a; }
   // Split-K over `S` CTAs per tile; `scratch` holds S fp32 copies of the output ([B][V][N] each). Call before finalize.
   void enable_splits(int S, float* scratch);

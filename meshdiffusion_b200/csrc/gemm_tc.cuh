@@ -93,6 +93,17 @@ struct GemmParams {
   int res_fp32;
   float alpha;
   long long* stats;  // [Bn][N][2] (sum, sumsq) in 2^-24 fixed point (order-independent accumulation) or null
+  // ---- GroupNorm-backward fusion (GNB instantiations; training data gradients). The accumulator is dL/da of a
+  // GroupNorm(+SiLU)(+dropout) output a = drop(act(gamma*xhat+beta)); `res` holds the GroupNorm INPUT x (columns
+  // >= res_c0 come from res1: the second source of a channel concatenation). The epilogue stores
+  // dy = da*drop*act'(y) and per-tile column partials of (sum dy, sum dy*xhat) for the GroupNorm backward.
+  const void* res1;
+  long long r1sx, r1sy, r1sz, r1sb;
+  int res_c0;
+  const float4* gnb_c;  // [Bn][N] {hsc, hsh, rs, nm}: y/2 = x*hsc + hsh, xhat = x*rs + nm
+  int gnb_silu;
+  int gnb_drop_thresh; float gnb_drop_scale; unsigned long long gnb_seed;
+  float* gnb_part;      // [tiles_m * bb][N][2]
 };
 
 template <int BLOCK_N, bool CG2>
@@ -109,6 +120,14 @@ struct GemmCfg {
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatsFloats * 4 +
                                     (2 * kStages + 4) * 8 + 16;
 };
+
+// dropout hash shared with the GroupNorm kernels (backward.cuh::drop_hash64)
+__device__ __forceinline__ unsigned long long gn_drop_hash64(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 
 // D[tmem] (+)= A * B with descriptors given as their low 32 bits (start address >> 4 | LBO) and a shared constant high
 // word (SBO = 1024 B, version 1, SWIZZLE_128B): all descriptor arithmetic is 32-bit adds on uniform values.
@@ -198,7 +217,9 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 // CG2 = CTA pair: the two CTAs of a 2-cluster own adjacent M-tiles; the leader's single thread issues
 // tcgen05.mma.cta_group::2 (M = 256) over both, each CTA stages its own A box and HALF of every weight tile, so the
 // per-SM L2->SMEM traffic, the shared-memory operand reads and the MMA issue count per FLOP all drop.
-template <int BLOCK_N, bool TF32, bool CG2>
+// GNB: GroupNorm-backward epilogue (see GemmParams::gnb_c) -- a separate instantiation, so the inference kernels'
+// code and register allocation are untouched.
+template <int BLOCK_N, bool TF32, bool CG2, bool GNB = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, CG2>;
   constexpr int NS = Cfg::kStages;
@@ -252,11 +273,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     lo = (int)((long long)p.total_groups * sidx / splits);
     hi = (int)((long long)p.total_groups * (sidx + 1) / splits);
   };
+  int mt_of_tile = 0;  // M-tile index of the last decoded work item (GNB partial rows)
   auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0) {
     tile /= splits;
     int nt = tile % p.n_tiles_n;
     int mt = tile / p.n_tiles_n;
     if (CG2) mt = 2 * mt + (int)rank;
+    mt_of_tile = mt;
     n0 = nt * BLOCK_N;
     if (mt >= tiles_m) {  // odd tile count: the pair's second CTA gets an empty tile (all loads zero-filled, no stores)
       x0 = 0; y0 = 0; z0 = 0; b0 = p.tb * p.bb;
@@ -432,6 +455,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       auto prefetch_res = [&](int ch) {
         const int nbp = n0 + ch * 32;
         if (!(p.res && valid && p.ocs == 1 && nbp + 32 <= p.N)) return;
+        if constexpr (GNB) {
+          // the GroupNorm input x: first or second source of the channel concatenation (32-column chunks never straddle)
+          const bool second = p.res1 && nbp >= p.res_c0;
+          const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(second ? p.res1 : p.res);
+          const long long off = second ? xg * p.r1sx + yg * p.r1sy + zg * p.r1sz + bg * p.r1sb + (nbp - p.res_c0) : roff + nbp;
+          const uint4* rp = reinterpret_cast<const uint4*>(base + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rbuf[i] = __ldg(rp + i);
+          return;
+        }
         if (TF32 || p.res_fp32) {
           const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.res) + roff + nbp);
 #pragma unroll
@@ -488,7 +521,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         const float* sb = s_bias + (seg < 4 ? seg : 0) * BLOCK_N + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) * p.alpha + mbias + sb[i];
-        if (p.res && valid) {
+        float q2[GNB ? 32 : 1];  // dy * xhat (GNB)
+        if constexpr (GNB) {
+          if (valid) {
+            const float4* cc = p.gnb_c + static_cast<long long>(bg) * p.N + nb;
+            unsigned long long hsh[8];
+            if (p.gnb_drop_thresh > 0) {
+              // same element index as the forward GroupNorm-apply kernel: ((b*V + voxel)*C + channel)
+              const unsigned long long e4 = (unsigned long long)((((static_cast<long long>(bg) * p.Z + zg) * p.Y + yg) * p.X + xg) * p.N + nb) >> 2;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hsh[i] = gn_drop_hash64(p.gnb_seed, e4 + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4 kc = __ldg(cc + i);
+              const __nv_bfloat16 xb = reinterpret_cast<const __nv_bfloat16*>(rbuf)[i];
+              const float xv = __bfloat162float(xb);
+              float d = v[i];
+              if (p.gnb_drop_thresh > 0) {
+                const unsigned r16 = (unsigned)((hsh[i >> 2] >> (16 * (i & 3))) & 0xFFFFu);
+                d = r16 >= (unsigned)p.gnb_drop_thresh ? d * p.gnb_drop_scale : 0.f;
+              }
+              if (p.gnb_silu) {
+                const float h = fmaf(xv, kc.x, kc.y);
+                float th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+                d *= fmaf(0.5f, h * fmaf(-th, th, 1.f), fmaf(0.5f, th, 0.5f));
+              }
+              v[i] = d;
+              q2[i] = d * fmaf(xv, kc.z, kc.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) q2[i] = 0.f;
+          }
+        }
+        if (!GNB && p.res && valid) {
           if (TF32 || p.res_fp32) {
             if (full) {
 #pragma unroll
@@ -547,14 +615,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
           }
         }
-        if (p.stats) {  // (never reached in split-K mode)
+        if (p.stats || (GNB && p.gnb_part)) {  // (never reached in split-K mode)
           // Column sums over the warp's 32 rows: butterfly transpose-reduce (31 shuffles per quantity);
           // afterwards lane i holds the sum of column i.
           float s[32], ss[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float t = valid ? v[i] : 0.f;
-            s[i] = t; ss[i] = t * t;
+            s[i] = t; ss[i] = GNB ? q2[GNB ? i : 0] : t * t;
           }
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
@@ -574,7 +642,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           s_part[(q * 2 + 1) * BLOCK_N + ch * 32 + lane] = ss[0];
         }
       }
-      if (p.stats && splits == 1) {
+      if constexpr (GNB) {
+        if (p.gnb_part && splits == 1) {
+          // per-tile column partials, one row per (M-tile, sample of the tile): summed in a fixed order by
+          // gnb_tile_reduce_kernel (deterministic gradients; no atomics)
+          named_bar_sync(1, kEpiThreads);
+          const int warps_per_seg = rows_per_b >= 128 ? 4 : rows_per_b / 32;
+          for (int i = et; i < p.bb * BLOCK_N; i += kEpiThreads) {
+            const int sg = i / BLOCK_N, c = i % BLOCK_N;
+            const int n = n0 + c;
+            if (mt_of_tile < tiles_m && n < p.N) {
+              float ts = 0.f, tq = 0.f;
+              for (int w = sg * warps_per_seg; w < (sg + 1) * warps_per_seg; ++w) {
+                ts += s_part[(w * 2 + 0) * BLOCK_N + c];
+                tq += s_part[(w * 2 + 1) * BLOCK_N + c];
+              }
+              float* dst = p.gnb_part + ((static_cast<long long>(mt_of_tile) * p.bb + sg) * p.N + n) * 2;
+              dst[0] = ts; dst[1] = tq;
+            }
+          }
+        }
+      }
+      if (!GNB && p.stats && splits == 1) {
         // the only barrier per tile: partials of tile i+1 go to the other buffer, and a buffer is rewritten two tiles
         // later, after every warp has passed this barrier once more
         named_bar_sync(1, kEpiThreads);

@@ -165,15 +165,22 @@ class UNet {
   Act act_of_grad(const GradView& g, int R) const;
   long long G(const std::string& name) const;  // offset of a parameter's gradient in the flat buffer
   struct Tmp { size_t off = 0; void* ptr = nullptr; };
+  // GroupNorm backward fused into the epilogue of the data-gradient GEMM that produces dL/d(GroupNorm output):
+  // filled in by the caller (which layer), completed by emit_conv_dgrad / emit_pointwise (whether it could be fused)
+  struct GnFuse {
+    std::string pname; std::vector<TensP> ins; bool silu = false; int drop_layer = -1;
+    bool on = false; Tmp consts, part; int T = 0, bb = 1;
+  };
+  void gn_fuse_attach(GnFuse& f, GemmOp* g, int N, int R);
   Tmp tmp_alloc(size_t bytes);
   void tmp_free(Tmp& t);
   GemmOp* new_bwd_gemm(const std::string& name);
   void emit_colsum(const std::string& name, const GradView& t, int R, float* per, long long per_ld, long long g0, long long g1, long long g2);
   void emit_wgrad(const std::string& name, const Act& dy, const Act& x, int ksize, int stride, long long goff, const WgradOut& layout);
-  GradView emit_conv_dgrad(const std::string& name, const GradView& dy, int R, const float* w, int cin_total, const GradView* addend);
-  GradView emit_pointwise(const std::string& name, const std::vector<Act>& srcs, const std::vector<WSrc>& ws, int N, int R, const GradView* addend);
+  GradView emit_conv_dgrad(const std::string& name, const GradView& dy, int R, const float* w, int cin_total, const GradView* addend, GnFuse* fuse = nullptr);
+  GradView emit_pointwise(const std::string& name, const std::vector<Act>& srcs, const std::vector<WSrc>& ws, int N, int R, const GradView* addend, GnFuse* fuse = nullptr);
   GradView emit_gn_backward(const std::string& pname, const std::vector<TensP>& ins, const GradView& da, bool silu, int drop_layer,
-                            const GradView* add0, const GradView* add1);
+                            const GradView* add0, const GradView* add1, GnFuse* fuse = nullptr);
   void tape_resblock(const std::vector<TensP>& ins, TensP a, TensP h, TensP a2, TensP out, int out_ch, int midx, int doff);
   void tape_attn(TensP x, TensP hn, TensP qkv, TensP S, TensP O, TensP out, int midx);
   void tape_downsample(TensP x, TensP out, int midx);

@@ -161,20 +161,56 @@ void UNet::emit_wgrad(const std::string& name, const Act& dy, const Act& x, int 
 }
 
 // data gradient of a stride-1 3^3 convolution: [C = cin_total] = conv(dy, W^T mirrored) (+ addend)
+// Sizes and attaches the GroupNorm-backward epilogue of a data-gradient GEMM (same decisions in the sizing pass, where
+// g == nullptr, and the real pass).
+void UNet::gn_fuse_attach(GnFuse& f, GemmOp* g, int N, int R) {
+  const int mb = cfg_.max_batch;
+  const Geometry geo = pick_geometry(R, R, R);
+  f.T = ((R + geo.bx - 1) / geo.bx) * ((R + geo.by - 1) / geo.by) * ((R + geo.bz - 1) / geo.bz);
+  f.bb = geo.bb;
+  const long long rows = 1LL * f.T * ((mb + geo.bb - 1) / geo.bb) * geo.bb;
+  f.consts = tmp_alloc((size_t)mb * N * 4 * sizeof(float));
+  f.part = tmp_alloc((size_t)rows * N * 2 * sizeof(float));
+  f.on = true;
+  if (dry_) return;
+  GnBwdArgs a{};
+  a.C0 = f.ins[0]->C; a.C1 = f.ins.size() > 1 ? f.ins[1]->C : 0;
+  a.stats0 = f.ins[0]->stats; a.stats1 = f.ins.size() > 1 ? f.ins[1]->stats : nullptr;
+  a.gamma = P(f.pname + ".weight", {N}); a.beta = P(f.pname + ".bias", {N});
+  a.voxels = (long long)R * R * R; a.groups = 32; a.eps = 1e-6f;
+  float* cp = (float*)f.consts.ptr;
+  add_bwd("gn_consts:" + f.pname, [a, cp](cudaStream_t s, int B) { launch_gn_consts(a, cp, B, s); });
+  g->set_gn_backward(f.ins[0]->ptr, f.ins[0]->C, f.ins[0]->C, f.ins.size() > 1 ? f.ins[1]->ptr : nullptr,
+                     f.ins.size() > 1 ? f.ins[1]->C : 0, f.consts.ptr, f.silu ? 1 : 0, (float*)f.part.ptr);
+  if (g->gnb_tiles_per_batch_tile() != f.T || g->gnb_bb() != f.bb) throw std::runtime_error("mdb: GroupNorm-backward tile plan mismatch");
+}
+
 GradView UNet::emit_conv_dgrad(const std::string& name, const GradView& dy, int R, const float* w, int cin_total,
-                               const GradView* addend) {
+                               const GradView* addend, GnFuse* fuse) {
   GradView dx = new_grad(cin_total, R);
   const bool can_split = !addend || addend->ld == cin_total;
   Scratch sp;
   if (can_split) sp = split_begin(R, cin_total, dy.C, 27);
+  const bool fused = fuse && !addend && sp.S <= 1 && cin_total % 32 == 0;
+  GemmOp* g = nullptr;
   if (!dry_) {
-    GemmOp* g = new_bwd_gemm(name);
+    g = new_bwd_gemm(name);
     g->set_output(prec_, R, R, R, cfg_.max_batch, cin_total, dx.ptr, cin_total, false);
     g->add_conv_dgrad(act_of_grad(dy, R), w, cin_total, 3);
     if (addend) g->set_residual(addend->ptr, addend->ld, (long long)R * R * R * addend->ld, false);
     g->enable_splits(sp.S, sp.ptr);
+  }
+  if (fused) gn_fuse_attach(*fuse, g, cin_total, R);
+  if (!dry_) {
     g->finalize(0, false);
-    add_bwd(name, [g](cudaStream_t s, int B) { g->launch(s, B); });
+    const int dl = fused ? fuse->drop_layer : -1;
+    add_bwd(name, [g, this, dl](cudaStream_t s, int B) {
+      if (dl >= 0) {
+        g->rt_drop_thresh = rt_drop_thresh_; g->rt_drop_scale = rt_drop_scale_;
+        g->rt_seed = rt_seed_ + 0x632BE59BD9B4E019ull * (unsigned long long)(dl + 1);
+      }
+      g->launch(s, B);
+    });
   }
   split_end(sp);
   return dx;
@@ -182,13 +218,18 @@ GradView UNet::emit_conv_dgrad(const std::string& name, const GradView& dy, int 
 
 // [N] = sum_i srcs[i] . ws[i]  (1x1x1 products accumulated in one TMEM accumulator) (+ addend)
 GradView UNet::emit_pointwise(const std::string& name, const std::vector<Act>& srcs, const std::vector<WSrc>& ws, int N, int R,
-                              const GradView* addend) {
+                              const GradView* addend, GnFuse* fuse) {
   GradView dx = new_grad(N, R);
+  const bool fused = fuse && !addend && N % 32 == 0;
+  GemmOp* g = nullptr;
   if (!dry_) {
-    GemmOp* g = new_bwd_gemm(name);
+    g = new_bwd_gemm(name);
     g->set_output(prec_, R, R, R, cfg_.max_batch, N, dx.ptr, N, false);
     for (size_t i = 0; i < srcs.size(); ++i) g->add_pointwise_w({srcs[i]}, &ws[i]);
     if (addend) g->set_residual(addend->ptr, addend->ld, (long long)R * R * R * addend->ld, false);
+  }
+  if (fused) gn_fuse_attach(*fuse, g, N, R);
+  if (!dry_) {
     g->finalize(0, false);
     add_bwd(name, [g](cudaStream_t s, int B) { g->launch(s, B); });
   }
@@ -196,14 +237,15 @@ GradView UNet::emit_pointwise(const std::string& name, const std::vector<Act>& s
 }
 
 GradView UNet::emit_gn_backward(const std::string& pname, const std::vector<TensP>& ins, const GradView& da, bool silu,
-                                int drop_layer, const GradView* add0, const GradView* add1) {
+                                int drop_layer, const GradView* add0, const GradView* add1, GnFuse* fuse) {
   int C = 0;
   for (auto& t : ins) C += t->C;
   const int R = ins[0]->R, mb = cfg_.max_batch;
   float* gamma = P(pname + ".weight", {C});
   float* beta = P(pname + ".bias", {C});
   if (da.ld != C) throw std::runtime_error("mdb: GroupNorm backward needs a dense upstream gradient");
-  Tmp part = tmp_alloc((size_t)kBwdPartRows(mb) * C * 2 * sizeof(float));
+  const bool fused = fuse && fuse->on;  // `da` already holds dy and the GEMM left per-tile partials: no pass 1
+  Tmp part = tmp_alloc(fused ? 16 : (size_t)kBwdPartRows(mb) * C * 2 * sizeof(float));
   Tmp sums = tmp_alloc((size_t)mb * C * 2 * sizeof(float));
   GradView dx = new_grad(C, R);
   // by-product of the apply pass: per-(sample, channel) sums of dx, kept with the buffer for the bias gradients of
@@ -235,12 +277,18 @@ GradView UNet::emit_gn_backward(const std::string& pname, const std::vector<Tens
       c.dgamma = rt_grads_ + gw; c.dbeta = rt_grads_ + gb; c.accumulate = rt_accum_ ? 1 : 0;
       return c;
     };
-    add_bwd("gn_bwd_reduce:" + pname, [with_rt](cudaStream_t s, int B) { launch_gn_bwd_reduce(with_rt(), B, s); });
+    if (fused) {
+      const float* tp = (const float*)fuse->part.ptr; const int T = fuse->T, bb = fuse->bb;
+      add_bwd("gnb_tile_reduce:" + pname, [with_rt, tp, T, bb](cudaStream_t s, int B) { launch_gnb_tile_reduce(with_rt(), tp, T, bb, B, s); });
+    } else {
+      add_bwd("gn_bwd_reduce:" + pname, [with_rt](cudaStream_t s, int B) { launch_gn_bwd_reduce(with_rt(), B, s); });
+    }
     add_bwd("gn_bwd_apply:" + pname, [with_rt](cudaStream_t s, int B) { launch_gn_bwd_apply(with_rt(), B, s); });
   }
   tmp_free(part);
   tmp_free(sums);
   tmp_free(cs_part);
+  if (fused) { tmp_free(fuse->consts); tmp_free(fuse->part); fuse->on = false; }
   return dx;
 }
 
@@ -280,9 +328,10 @@ void UNet::tape_resblock(const std::vector<TensP>& ins, TensP a, TensP h, TensP 
         coff += t->C;
       }
     }
-    GradView da2 = emit_conv_dgrad(nm + ".conv1.dgrad", dO, R, w1, out_ch, nullptr);
+    GnFuse f1; f1.pname = pre + "GroupNorm_1"; f1.ins = {h}; f1.silu = true; f1.drop_layer = midx;
+    GradView da2 = emit_conv_dgrad(nm + ".conv1.dgrad", dO, R, w1, out_ch, nullptr, &f1);
     free_act(a2);
-    GradView dh = emit_gn_backward(pre + "GroupNorm_1", {h}, da2, true, midx, nullptr, nullptr);
+    GradView dh = emit_gn_backward(pre + "GroupNorm_1", {h}, da2, true, midx, nullptr, nullptr, &f1);
     unref(da2);
     // Conv_0 bias and the time-embedding projection: h += Dense_0(act(temb))[:, :, None, None, None]
     emit_colsum(nm + ".conv0.dbias", dh, R, dry_ ? nullptr : d_dense_out_ + doff, dense_total_, G(pre + "Conv_0.bias"), -1, -1);
@@ -295,14 +344,15 @@ void UNet::tape_resblock(const std::vector<TensP>& ins, TensP a, TensP h, TensP 
     }
     emit_wgrad(nm + ".conv0.wgrad", act_of_grad(dh, R), act_of(a), 3, 1, G(pre + "Conv_0.weight"), oidhw_layout(Cin));
     free_act(a);
-    GradView da = emit_conv_dgrad(nm + ".conv0.dgrad", dh, R, w0, Cin, nullptr);
+    GnFuse f0; f0.pname = pre + "GroupNorm_0"; f0.ins = ins; f0.silu = true; f0.drop_layer = -1;
+    GradView da = emit_conv_dgrad(nm + ".conv0.dgrad", dh, R, w0, Cin, nullptr, &f0);
     unref(dh);
     free_act(h);
     // shortcut: identity -> dO itself; NIN -> dO . W^T
     GradView sc;
     if (nin) sc = emit_pointwise(nm + ".nin.dgrad", {act_of_grad(dO, R)}, {WSrc{wn, (long long)out_ch, 1, 0, out_ch}}, Cin, R, nullptr);
     GradView prev = ins.size() == 1 ? ins[0]->grad : GradView{};
-    GradView dx = emit_gn_backward(pre + "GroupNorm_0", ins, da, true, -1, nin ? &sc : &dO, prev.valid() ? &prev : nullptr);
+    GradView dx = emit_gn_backward(pre + "GroupNorm_0", ins, da, true, -1, nin ? &sc : &dO, prev.valid() ? &prev : nullptr, &f0);
     unref(da);
     if (nin) unref(sc);
     unref(out->grad);
@@ -415,10 +465,11 @@ void UNet::tape_attn(TensP x, TensP hn, TensP qkv, TensP S, TensP O, TensP out, 
     }
     free_act(hn);
     free_act(qkv);
-    GradView dhn = emit_pointwise(nm + ".qkv.dgrad", parts, wsv, C, R, nullptr);
+    GnFuse fa; fa.pname = pre + "GroupNorm_0"; fa.ins = {x}; fa.silu = false; fa.drop_layer = -1;
+    GradView dhn = emit_pointwise(nm + ".qkv.dgrad", parts, wsv, C, R, nullptr, &fa);
     unref(dqkv);
     GradView prev = x->grad;
-    GradView dx = emit_gn_backward(pre + "GroupNorm_0", {x}, dhn, false, -1, &dO, prev.valid() ? &prev : nullptr);
+    GradView dx = emit_gn_backward(pre + "GroupNorm_0", {x}, dhn, false, -1, &dO, prev.valid() ? &prev : nullptr, &fa);
     unref(dhn);
     unref(out->grad);
     if (prev.valid()) unref(x->grad);
@@ -543,9 +594,10 @@ void UNet::tape_head(TensP h, TensP a, const std::string& gn_name, const std::st
     }
     free_act(a);
     WSrc wd{hw + (T - 1), (long long)T, -1, 0, Cin * T, 0, 0, T, (long long)nf * T};
-    GradView da = emit_pointwise("head.dgrad", {ada}, {wd}, nf, R0, nullptr);
+    GnFuse fh; fh.pname = gn_name; fh.ins = {h}; fh.silu = true; fh.drop_layer = -1;
+    GradView da = emit_pointwise("head.dgrad", {ada}, {wd}, nf, R0, nullptr, &fh);
     tmp_free(Ad);
-    GradView dx = emit_gn_backward(gn_name, {h}, da, true, -1, nullptr, nullptr);
+    GradView dx = emit_gn_backward(gn_name, {h}, da, true, -1, nullptr, nullptr, &fh);
     unref(da);
     if (h->grad.valid()) throw std::runtime_error("mdb: head input already has a gradient");
     h->grad = dx;
