@@ -6,6 +6,7 @@
 // planner as the inference engine.
 #include "unet.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace mdb {
 
@@ -161,6 +162,12 @@ void UNet::emit_wgrad(const std::string& name, const Act& dy, const Act& x, int 
 }
 
 // data gradient of a stride-1 3^3 convolution: [C = cin_total] = conv(dy, W^T mirrored) (+ addend)
+// MDB_GNB=0 keeps the two-pass GroupNorm backward everywhere (A/B comparisons; tests compare both paths under dropout)
+static bool gnb_enabled() {
+  const char* e = getenv("MDB_GNB");
+  return !(e && e[0] == '0');
+}
+
 // Sizes and attaches the GroupNorm-backward epilogue of a data-gradient GEMM (same decisions in the sizing pass, where
 // g == nullptr, and the real pass).
 void UNet::gn_fuse_attach(GnFuse& f, GemmOp* g, int N, int R) {
@@ -191,7 +198,7 @@ GradView UNet::emit_conv_dgrad(const std::string& name, const GradView& dy, int 
   const bool can_split = !addend || addend->ld == cin_total;
   Scratch sp;
   if (can_split) sp = split_begin(R, cin_total, dy.C, 27);
-  const bool fused = fuse && !addend && sp.S <= 1 && cin_total % 32 == 0;
+  const bool fused = fuse && gnb_enabled() && !addend && sp.S <= 1 && cin_total % 32 == 0;
   GemmOp* g = nullptr;
   if (!dry_) {
     g = new_bwd_gemm(name);
@@ -220,7 +227,7 @@ GradView UNet::emit_conv_dgrad(const std::string& name, const GradView& dy, int 
 GradView UNet::emit_pointwise(const std::string& name, const std::vector<Act>& srcs, const std::vector<WSrc>& ws, int N, int R,
                               const GradView* addend, GnFuse* fuse) {
   GradView dx = new_grad(N, R);
-  const bool fused = fuse && !addend && N % 32 == 0;
+  const bool fused = fuse && gnb_enabled() && !addend && N % 32 == 0;
   GemmOp* g = nullptr;
   if (!dry_) {
     g = new_bwd_gemm(name);

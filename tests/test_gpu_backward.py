@@ -338,3 +338,36 @@ def test_res64_full_backward_vs_autograd():
     worst = max(((n, (num / den) ** 0.5) for n, num, den in rows if den > 1e-8 * tot_den), key=lambda t: t[1])
     print(f"res64 full: loss {loss.item():.5f} vs {ref_loss.item():.5f}; {len(rows)} tensors, global rel-l2 {glob:.3e}, worst {worst[0]} {worst[1]:.3e}")
     assert glob < 4e-2 and worst[1] < 1.5e-1
+
+
+def test_dropout_gradients_fused_vs_two_pass(monkeypatch):
+    """Dropout masks come from a counter hash of (seed, layer, element) evaluated in three places: the forward
+    GroupNorm-apply kernel, the two-pass GroupNorm backward, and the fused GEMM epilogue. With a fixed seed the fused and
+    the two-pass engines must therefore produce the same gradients (up to bf16 rounding of dy), which pins the element
+    indexing of all three against each other; and the gradients must differ from the no-dropout ones."""
+    import ctypes
+    from meshdiffusion_b200 import _native
+    cfg = tiny_config("res64", "bf16")
+    cfg.model.dropout = 0.3
+    R, B = 16, 2
+
+    def grads(fused, p):
+        monkeypatch.setenv("MDB_GNB", "1" if fused else "0")
+        torch.manual_seed(1234)  # the dropout seed derives from torch.initial_seed() and a per-model call counter
+        cfg.model.dropout = p
+        model, sd = build_model(cfg, "cuda:0", 3)
+        net = model.module
+        net.train()
+        x, labels = synth.synthetic_inputs(R, B, 8, sd["mask"])
+        model(x.cuda(), labels.cuda()).square().mean().backward()
+        g = net._flat_grad.clone()
+        net.release_engine()
+        return g
+
+    g_fused, g_two = grads(True, 0.3), grads(False, 0.3)
+    g_none = grads(True, 0.0)
+    rel = (g_fused - g_two).norm().item() / g_two.norm().item()
+    away = (g_fused - g_none).norm().item() / g_none.norm().item()
+    print(f"fused vs two-pass under dropout: rel-l2 {rel:.3e}; dropout vs none: {away:.3e}")
+    assert rel < 1e-2
+    assert away > 5e-2
