@@ -216,6 +216,15 @@ void launch_gn_bwd_reduce(const GnBwdArgs& a, int B, cudaStream_t s) {
   MDB_LAUNCH_CHECK();
 }
 
+constexpr int kApplyDepth = 4;
+constexpr int kApplySmem = kApplyDepth * 4 * 256 * 16;  // 64 KB
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
   __shared__ float red[256 * VEC];
   const int C = a.C0 + a.C1;
@@ -263,23 +272,36 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
 #pragma unroll
   for (int j = 0; j < VEC; ++j) cs[j] = 0.f;
   const long long step = (long long)gridDim.x * k;
-  // software pipeline: the loads of voxel i+1 are issued before voxel i is processed, so every warp always has a full
-  // set of requests in flight (the kernel is latency-bound at 2 blocks/SM otherwise: ncu, profiles/r01_ncu_prof_gn_backward.txt)
-  uint4 cx, cd, c0r, c1r;
-  long long v = (long long)blockIdx.x * k + vl;
-  auto issue = [&](long long vv, uint4& qx, uint4& qd, uint4& q0, uint4& q1) {
-    q0 = make_uint4(0, 0, 0, 0); q1 = make_uint4(0, 0, 0, 0);
+  // cp.async ring: every thread keeps kApplyDepth voxels of its own loads in flight in a private shared-memory slot
+  // ring (no barriers: a thread only ever reads what it copied itself). The register-staged version of this kernel was
+  // latency-bound at ~1.9 TB/s (ncu: 7 warps stalled on long-scoreboard per issue, 25-37 % occupancy); with 3 blocks/SM
+  // and 4 stages there are up to 190 KB of requests outstanding per SM.
+  extern __shared__ uint4 ring[];  // [kApplyDepth][4 streams][256 threads]
+  const int nstreams = 2 + (p0 ? 1 : 0) + (p1 ? 1 : 0);
+  auto slot = [&](int stage, int stream) { return ring + ((stage * 4 + stream) * 256 + threadIdx.x); };
+  auto issue = [&](long long vv, int stage) {
     if (vv < a.voxels) {
-      qx = __ldg((const uint4*)(src + vv * src_stride));
-      qd = *((const uint4*)(dsrc + vv * d_stride));  // written by pass 1 of this very step: no read-only path
-      if (p0) q0 = __ldg((const uint4*)(p0 + vv * a.add0_ld * 2));
-      if (p1) q1 = __ldg((const uint4*)(p1 + vv * a.add1_ld * 2));
+      cp_async16(slot(stage, 0), src + vv * src_stride);
+      cp_async16(slot(stage, 1), dsrc + vv * d_stride);
+      if (p0) cp_async16(slot(stage, 2), p0 + vv * a.add0_ld * 2);
+      if (p1) cp_async16(slot(stage, 3), p1 + vv * a.add1_ld * 2);
     }
+    cp_async_commit();
   };
-  issue(v, cx, cd, c0r, c1r);
+  (void)nstreams;
+  long long v = (long long)blockIdx.x * k + vl;
+#pragma unroll
+  for (int d = 0; d < kApplyDepth - 1; ++d) issue(v + d * step, d);
+  int stage = 0;
   for (; v < a.voxels; v += step) {
-    uint4 nx, nd, n0, n1;
-    issue(v + step, nx, nd, n0, n1);
+    int nst = stage + kApplyDepth - 1;
+    if (nst >= kApplyDepth) nst -= kApplyDepth;
+    issue(v + (long long)(kApplyDepth - 1) * step, nst);
+    cp_async_wait<kApplyDepth - 1>();
+    const uint4 cx = *slot(stage, 0), cd = *slot(stage, 1);
+    uint4 c0r = make_uint4(0, 0, 0, 0), c1r = make_uint4(0, 0, 0, 0);
+    if (p0) c0r = *slot(stage, 2);
+    if (p1) c1r = *slot(stage, 3);
     float x[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
     unpack8(cx, x); unpack8(cd, dy); unpack8(c0r, e0); unpack8(c1r, e1);
 #pragma unroll
@@ -288,8 +310,9 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
       cs[j] += o[j];
     }
     *((uint4*)(dst + v * d_stride)) = pack8(o);
-    cx = nx; cd = nd; c0r = n0; c1r = n1;
+    if (++stage == kApplyDepth) stage = 0;
   }
+  cp_async_wait<0>();
   if (a.cs_part) {  // per-(sample, channel) column sums of dx for the bias / time-embedding gradients downstream
 #pragma unroll
     for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = cs[j];
@@ -317,7 +340,12 @@ void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s) {
   gn_launch_shape(a, cv, k);
   const int C = a.C0 + a.C1;
   const int gx = blocks_x(a.voxels, k, B, 444);
-  gn_bwd_apply_kernel<<<dim3((unsigned)gx, B), cv * k, 0, s>>>(a, cv, k);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
+    configured = true;
+  }
+  gn_bwd_apply_kernel<<<dim3((unsigned)gx, B), cv * k, kApplySmem, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
   if (a.cs_part) {
     cs_final_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a.cs_part, a.cs_per, gx, B * C);
