@@ -225,6 +225,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// NADD = number of addend streams (0, 1, 2): absent streams cost no instructions (GroupNorm_1 layers have none)
+template <int NADD>
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int cv, int k) {
   __shared__ float red[256 * VEC];
   const int C = a.C0 + a.C1;
@@ -266,8 +268,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
   const char* dsrc = (const char*)a.da + ((long long)b * a.voxels * C + c) * 2;
   const long long d_stride = (long long)C * 2;
   char* dst = (char*)a.dx + ((long long)b * a.voxels * C + c) * 2;
-  const char* p0 = a.add0 ? (const char*)a.add0 + ((long long)b * a.voxels * a.add0_ld + c) * 2 : nullptr;
-  const char* p1 = a.add1 ? (const char*)a.add1 + ((long long)b * a.voxels * a.add1_ld + c) * 2 : nullptr;
+  const char* p0 = NADD >= 1 ? (const char*)a.add0 + ((long long)b * a.voxels * a.add0_ld + c) * 2 : nullptr;
+  const char* p1 = NADD >= 2 ? (const char*)a.add1 + ((long long)b * a.voxels * a.add1_ld + c) * 2 : nullptr;
   float cs[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) cs[j] = 0.f;
@@ -277,18 +279,16 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
   // latency-bound at ~1.9 TB/s (ncu: 7 warps stalled on long-scoreboard per issue, 25-37 % occupancy); with 3 blocks/SM
   // and 4 stages there are up to 190 KB of requests outstanding per SM.
   extern __shared__ uint4 ring[];  // [kApplyDepth][4 streams][256 threads]
-  const int nstreams = 2 + (p0 ? 1 : 0) + (p1 ? 1 : 0);
   auto slot = [&](int stage, int stream) { return ring + ((stage * 4 + stream) * 256 + threadIdx.x); };
   auto issue = [&](long long vv, int stage) {
     if (vv < a.voxels) {
       cp_async16(slot(stage, 0), src + vv * src_stride);
       cp_async16(slot(stage, 1), dsrc + vv * d_stride);
-      if (p0) cp_async16(slot(stage, 2), p0 + vv * a.add0_ld * 2);
-      if (p1) cp_async16(slot(stage, 3), p1 + vv * a.add1_ld * 2);
+      if (NADD >= 1) cp_async16(slot(stage, 2), p0 + vv * a.add0_ld * 2);
+      if (NADD >= 2) cp_async16(slot(stage, 3), p1 + vv * a.add1_ld * 2);
     }
     cp_async_commit();
   };
-  (void)nstreams;
   long long v = (long long)blockIdx.x * k + vl;
 #pragma unroll
   for (int d = 0; d < kApplyDepth - 1; ++d) issue(v + d * step, d);
@@ -299,16 +299,24 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
     issue(v + (long long)(kApplyDepth - 1) * step, nst);
     cp_async_wait<kApplyDepth - 1>();
     const uint4 cx = *slot(stage, 0), cd = *slot(stage, 1);
-    uint4 c0r = make_uint4(0, 0, 0, 0), c1r = make_uint4(0, 0, 0, 0);
-    if (p0) c0r = *slot(stage, 2);
-    if (p1) c1r = *slot(stage, 3);
-    float x[VEC], dy[VEC], e0[VEC], e1[VEC], o[VEC];
-    unpack8(cx, x); unpack8(cd, dy); unpack8(c0r, e0); unpack8(c1r, e1);
+    float x[VEC], dy[VEC], o[VEC];
+    unpack8(cx, x); unpack8(cd, dy);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      o[j] = fmaf(-x[j], k1[j], fmaf(c1[j], dy[j], -k0[j])) + e0[j] + e1[j];
-      cs[j] += o[j];
+    for (int j = 0; j < VEC; ++j) o[j] = fmaf(-x[j], k1[j], fmaf(c1[j], dy[j], -k0[j]));
+    if (NADD >= 1) {
+      float e[VEC];
+      unpack8(*slot(stage, 2), e);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] += e[j];
     }
+    if (NADD >= 2) {
+      float e[VEC];
+      unpack8(*slot(stage, 3), e);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] += e[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) cs[j] += o[j];
     *((uint4*)(dst + v * d_stride)) = pack8(o);
     if (++stage == kApplyDepth) stage = 0;
   }
@@ -342,10 +350,17 @@ void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s) {
   const int gx = blocks_x(a.voxels, k, B, 444);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
+    cudaFuncSetAttribute(gn_bwd_apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
+    cudaFuncSetAttribute(gn_bwd_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
+    cudaFuncSetAttribute(gn_bwd_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
     configured = true;
   }
-  gn_bwd_apply_kernel<<<dim3((unsigned)gx, B), cv * k, kApplySmem, s>>>(a, cv, k);
+  GnBwdArgs q = a;
+  if (!q.add0 && q.add1) { q.add0 = q.add1; q.add0_ld = q.add1_ld; q.add1 = nullptr; }  // streams are filled front to back
+  const dim3 grid((unsigned)gx, B);
+  if (q.add1) gn_bwd_apply_kernel<2><<<grid, cv * k, kApplySmem, s>>>(q, cv, k);
+  else if (q.add0) gn_bwd_apply_kernel<1><<<grid, cv * k, kApplySmem, s>>>(q, cv, k);
+  else gn_bwd_apply_kernel<0><<<grid, cv * k, kApplySmem, s>>>(q, cv, k);
   MDB_LAUNCH_CHECK();
   if (a.cs_part) {
     cs_final_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a.cs_part, a.cs_per, gx, B * C);

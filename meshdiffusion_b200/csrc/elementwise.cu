@@ -354,7 +354,39 @@ __global__ void transpose_vc_kernel(const T* __restrict__ in, long long ld, int 
     if (v < V && c < C) out[((long long)b * C + c) * V + v] = tile[threadIdx.x][j];
   }
 }
+// bf16 fast path: 64x64 tiles, two elements (4 bytes) per thread on both the read and the write side, so every warp
+// moves full 128-byte rows (the 32x32 / 2-byte version touched half-used sectors in both directions)
+__global__ void __launch_bounds__(256) transpose_vc_bf16x2_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int c0,
+                                                                  __nv_bfloat16* __restrict__ out, int V, int C) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int b = blockIdx.z;
+  const int v0 = blockIdx.x * 64, cb = blockIdx.y * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 64; j += 8) {
+    const int v = v0 + j, c = cb + 2 * tx;
+    if (v < V && c + 1 < C) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(in + ((long long)b * V + v) * ld + c0 + c);
+      tile[j][2 * tx] = t.x; tile[j][2 * tx + 1] = t.y;
+    }
+  }
+  __syncthreads();
+  for (int j = ty; j < 64; j += 8) {
+    const int c = cb + j, v = v0 + 2 * tx;
+    if (c < C && v + 1 < V) {
+      __nv_bfloat162 t;
+      t.x = tile[2 * tx][j]; t.y = tile[2 * tx + 1][j];
+      *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * C + c) * V + v) = t;
+    }
+  }
+}
+
 void launch_transpose_vc(const void* in, long long ld, int c0, void* out, int B, int V, int C, int tf32, cudaStream_t s) {
+  if (!tf32 && V % 64 == 0 && C % 64 == 0 && ld % 2 == 0 && c0 % 2 == 0) {
+    dim3 grid(V / 64, C / 64, B), block(32, 8);
+    transpose_vc_bf16x2_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C);
+    MDB_LAUNCH_CHECK();
+    return;
+  }
   dim3 grid((V + 31) / 32, (C + 31) / 32, B), block(32, 8);
   if (tf32) transpose_vc_kernel<float><<<grid, block, 0, s>>>((const float*)in, ld, c0, (float*)out, V, C);
   else transpose_vc_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C);
