@@ -118,6 +118,12 @@ int mdb_adam_ema_step(float* const* params_dev, const float* const* grads_dev, f
                       float beta1, float beta2, float eps, int step, const float* clip_coef_dev, float ema_decay,
                       void* stream);
 
+/* Data-parallel training: mean all-reduce of the flat gradient buffer (what mdb_unet_backward filled) over the caller's
+ * NCCL communicator (ncclComm_t passed as void*), in place, on `stream`; replaces nn.DataParallel's gradient gather
+ * (lib/diffusion/models/utils.py:95). NCCL is taken from the libnccl.so.2 already loaded in the process. The Python
+ * host of this repository uses torch.distributed.all_reduce on the same buffer instead (torch owns its communicator). */
+int mdb_allreduce_grads(void* nccl_comm, float* grads, long long numel, int world_size, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Operator-level entry points (parity tests call these like the reference's renderutils tests call its ops).
  * Activations are NDHWC in the operand dtype of `precision` (bf16 or fp32).

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mdb_ddpm_loss": (_i, [_vp, _vp, _vp, _d, _vp, _vp, _vp, _i, _i, _ll, _vp]),
     "mdb_grad_clip_coef": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "mdb_adam_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _i, _vp, _f, _vp]),
+    "mdb_allreduce_grads": (_i, [_vp, _vp, _ll, _i, _vp]),
     "mdb_conv3d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "mdb_groupnorm_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp]),
     "mdb_conv3d_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

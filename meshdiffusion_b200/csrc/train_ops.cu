@@ -2,9 +2,10 @@
 // lib/diffusion/models/ema.py:43-64): the masked DDPM loss with its gradient, global-norm gradient clipping, and a
 // single multi-tensor pass that applies clipping + Adam + the EMA update (the reference makes ~5 separate passes over
 // the 364 M parameters per step: clip_grad_norm_, Adam's foreach ops, EMA).
-// These are the optimiser-side building blocks of the training step; the network backward pass is not built yet.
+// These are the optimiser-side building blocks of the training step (the network backward is unet_train.cu).
 #include "../../include/meshdiff_b200.h"
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdexcept>
 #include <string>
 
@@ -144,6 +145,35 @@ int mdb_adam_ema_step(float* const* params_dev, const float* const* grads_dev, f
   a.clip_coef = clip_coef_dev;
   adam_ema_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(a);
   TR_CHECK(cudaGetLastError());
+  TR_API_END
+}
+
+// ---- data-parallel gradient exchange over a caller-owned NCCL communicator. NCCL is resolved at call time from the
+// library already loaded in the process (the host created the communicator with it), so this shared object carries no
+// link-time dependency on a particular libnccl.
+__global__ void scale_kernel(float* p, float f, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] *= f;
+}
+
+int mdb_allreduce_grads(void* nccl_comm, float* grads, long long numel, int world_size, void* stream) {
+  TR_API_BEGIN
+  if (!nccl_comm || world_size < 1) throw std::runtime_error("mdb: mdb_allreduce_grads needs a communicator and its size");
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static allreduce_fn fn = nullptr;
+  if (!fn) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw std::runtime_error("mdb: libnccl.so.2 is not loadable");
+    fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    if (!fn) throw std::runtime_error("mdb: ncclAllReduce not found");
+  }
+  const int ncclFloat32 = 7, ncclSum = 0;  // nccl.h enums (stable since NCCL 2.0)
+  const int rc = fn(grads, grads, (size_t)numel, ncclFloat32, ncclSum, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) throw std::runtime_error("mdb: ncclAllReduce failed with code " + std::to_string(rc));
+  if (world_size > 1) {
+    scale_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(grads, 1.f / (float)world_size, numel);
+    TR_CHECK(cudaGetLastError());
+  }
   TR_API_END
 }
 

@@ -51,3 +51,25 @@ def test_fused_adam_ema_matches_torch():
             assert torch.allclose(q, p, rtol=2e-6, atol=1e-9)
         for s, e in zip(ema_ref.shadow_params, ema_ours):
             assert torch.allclose(e, s, rtol=2e-6, atol=1e-9)
+
+
+def test_allreduce_grads_over_caller_communicator():
+    """mdb_allreduce_grads drives ncclAllReduce on a communicator the HOST created (here a 1-rank communicator made through
+    ctypes on the process's libnccl): sum over the ranks, then the mean scaling by the world size the caller states."""
+    import ctypes
+    from meshdiffusion_b200 import _native
+    L = _native.lib()
+    nccl = ctypes.CDLL("libnccl.so.2")
+    comm = ctypes.c_void_p()
+    dev = (ctypes.c_int * 1)(torch.cuda.current_device())
+    assert nccl.ncclCommInitAll(ctypes.byref(comm), 1, dev) == 0
+    try:
+        g = torch.arange(1000, device="cuda", dtype=torch.float32)
+        _native.check(L.mdb_allreduce_grads(comm, _native.ptr(g), g.numel(), 1, _native.current_stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(g, torch.arange(1000, device="cuda", dtype=torch.float32))
+        _native.check(L.mdb_allreduce_grads(comm, _native.ptr(g), g.numel(), 2, _native.current_stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(g, torch.arange(1000, device="cuda", dtype=torch.float32) * 0.5)
+    finally:
+        nccl.ncclCommDestroy(comm)
