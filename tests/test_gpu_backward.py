@@ -371,3 +371,29 @@ def test_dropout_gradients_fused_vs_two_pass(monkeypatch):
     print(f"fused vs two-pass under dropout: rel-l2 {rel:.3e}; dropout vs none: {away:.3e}")
     assert rel < 1e-2
     assert away > 5e-2
+
+
+def test_backward_with_smaller_runtime_batch():
+    """An engine planned for batch 4 must give, for a batch of 2, exactly the gradients of an engine planned for 2
+    (weight-gradient tensor maps / split plans and the tile-partial rows are re-derived per runtime batch)."""
+    cfg = tiny_config("res64", "bf16")
+    cfg.model.dropout = 0.0
+    R = 16
+
+    def run(first_batch):
+        model, sd = build_model(cfg, "cuda:0", 3)
+        net = model.module
+        net.train()
+        x, labels = synth.synthetic_inputs(R, 4, 8, sd["mask"])
+        x, labels = x.cuda(), labels.cuda()
+        if first_batch == 4:
+            model(x, labels).square().mean().backward()
+            for p in net.parameters():
+                p.grad = None
+        model(x[:2].contiguous(), labels[:2].contiguous()).square().mean().backward()
+        g = net._flat_grad.clone()
+        net.release_engine()
+        return g
+
+    g4, g2 = run(4), run(2)
+    assert torch.equal(g4, g2)
