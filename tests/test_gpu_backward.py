@@ -400,3 +400,46 @@ def test_backward_with_smaller_runtime_batch():
     rel = (g4 - g2).norm().item() / g2.norm().item()
     print(f"planned-4 vs planned-2 engines on a batch of 2: rel-l2 {rel:.3e}")
     assert rel < 1e-2
+
+
+def test_res64_full_loss_curve_tracks_fp32_reference():
+    """The 20-step tiny-network experiment at the real size: 8 Adam steps of the full res64 network (batch 2, dropout off)
+    on the engine vs fp32 autograd through the oracle with identical data, labels and noise."""
+    from helpers import ddpm_loss, full_config
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = full_config("res64", "bf16")
+    cfg.model.dropout = 0.0
+    model, sd = build_model(cfg, "cuda:0", 5)
+    net = model.module
+    net.train()
+    R, B, steps = 64, 2, 8
+    mask = sd["mask"].cuda().view(1, 1, R, R, R)
+    arch = unet_oracle.arch_from_config(cfg)
+    ref_sd = {k: (v.cuda().clone().requires_grad_(True) if v.dtype == torch.float32 and k not in ("mask", "coords") else v.cuda()) for k, v in sd.items()}
+    ref_params = [v for v in ref_sd.values() if v.requires_grad]
+    opt_ref = torch.optim.Adam(ref_params, lr=1e-4)
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    data = (torch.rand(B, 4, R, R, R, device="cuda", generator=g) * 2 - 1) * mask
+    ours, theirs = [], []
+    for it in range(steps):
+        labels = torch.randint(0, 1000, (B,), device="cuda", generator=g).float()
+        noise = torch.randn(data.shape, device="cuda", generator=g)
+        x = (0.7 * data + 0.7 * noise) * mask
+        opt_ref.zero_grad()
+        lr_ = ddpm_loss(unet_oracle.unet_forward(ref_sd, arch, x, labels), noise, mask)
+        lr_.backward()
+        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        opt_ref.step()
+        opt.zero_grad()
+        lo = ddpm_loss(model(x, labels), noise, mask)
+        lo.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in net.parameters() if p.requires_grad], 1.0)
+        opt.step()
+        ours.append(lo.item()); theirs.append(lr_.item())
+    print("engine:", " ".join(f"{v:.4f}" for v in ours))
+    print("fp32  :", " ".join(f"{v:.4f}" for v in theirs))
+    rel = max(abs(a - b) / abs(b) for a, b in zip(ours, theirs))
+    print(f"max relative loss difference over {steps} full-size steps: {rel:.3e}")
+    assert rel < 1e-2
