@@ -239,6 +239,20 @@ def run_ours(args):
         other = {"dtype": "tf32", "value": world * B * K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K}
         net2.release_engine()
 
+    # ---- secondary: one training step (BASELINE configs[2]) through tools/bench_train.py in a fresh process
+    train = None
+    if rank == 0 and world == 1 and not args.no_train_leg and R == 64:
+        import subprocess
+        torch.cuda.empty_cache()
+        try:
+            r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_train.py"),
+                                "--batch", "16", "--iters", "1", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+            t = json.loads(r.stdout.strip().splitlines()[-1])
+            train = {"value": t["value"], "unit": t["unit"], "workload": t["config"]["workload"], "split_ms_per_step": t["split_ms_per_step"],
+                     "fwd_bwd_tflops": t["roofline"]["achieved"], "fwd_bwd_frac_of_peak": t["roofline"]["frac"]}
+        except Exception as ex:  # informational leg: never fails the bench line
+            train = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC if R == 64 else METRIC.replace("res-64 (4x64^3)", "res-128 (4x128^3)"), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -252,7 +266,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(K * (launches_per_forward + 2)) if launches_per_forward else None,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "tf32_operands": other,
-            "engine": info,
+            "engine": info, "train": train,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -370,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tf32-leg", action="store_true", help="skip the secondary TF32-operand measurement")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the secondary training-step measurement (tools/bench_train.py)")
     ap.add_argument("--dump-profile", default=None, help="write the per-launch CUDA-event times of one forward as JSON")
     args = ap.parse_args()
     if args.batch is None:
