@@ -75,6 +75,9 @@ int mdb_unet_set_dropout(mdb_unet* net, float p, unsigned long long seed);
 int mdb_unet_backward(mdb_unet* net, const float* dout, float* grads, long long grads_numel, int batch, int accumulate,
                       void* stream);
 int mdb_unet_grad_offset(mdb_unet* net, const char* name, long long* offset);
+/* Diagnostics: copies the raw GroupNorm statistics of the last forward to the host (split fixed-point records (sum lo, sum hi,
+ * sumsq lo, sumsq hi), per tensor [B][C][4] in plan order); synchronises. count receives the number of int64 values. */
+int mdb_unet_debug_stats(mdb_unet* net, long long* host_out, long long capacity, long long* count);
 int mdb_unet_train_info(mdb_unet* net, double* bwd_flops_per_sample, int* n_bwd_steps, long long* total_param_numel);
 /* One profiled backward (same contract as mdb_unet_profile). */
 int mdb_unet_profile_backward(mdb_unet* net, const float* dout, float* grads, int batch, void* stream, char* names_buf,
@@ -130,12 +133,13 @@ int mdb_allreduce_grads(void* nccl_comm, float* grads, long long numel, int worl
  */
 /* nn.Conv3d k in {1,3,5}, stride 1 (padding k/2) or stride 2 (Downsample: pad-high + VALID, layers.py:626-643).
  * x: [B][Z][Y][X][Cin] (input extents), w: fp32 OIDHW, y: [B][Zo][Yo][Xo][Cout]. Optional: bias [Cout],
- * rowbias [B][Cout], residual (same layout as y), stats [B][Cout][2] int64 = (sum, sum of squares) of the result in
- * 2^-24 fixed point, accumulated with integer atomics (must be zeroed by the caller). */
+ * rowbias [B][Cout], residual (same layout as y), stats [B][Cout][4] int64 = (sum, sum of squares) of the result as
+ * split fixed-point pairs, value = w_lo * 2^-24 + w_hi * 2^16 (csrc/gn_stats.cuh: exact, order-independent, cannot
+ * overflow), accumulated with integer atomics (must be zeroed by the caller). */
 int mdb_conv3d(const void* x, int batch, int cin, int z, int y_, int x_, const float* w, const float* bias, int cout,
                int ksize, int stride, void* out, const float* rowbias, const void* residual, long long* stats,
                int precision, void* stream);
-/* GroupNorm(32, eps=1e-6) [+ SiLU] from channel statistics: x [B][V][C], stats [B][C][2] (fixed point, as above),
+/* GroupNorm(32, eps=1e-6) [+ SiLU] from channel statistics: x [B][V][C], stats [B][C][4] (split fixed point, as above),
  * y [B][V][C]. */
 int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma, const float* beta, void* y, int batch,
                       long long voxels, int channels, int silu, int precision, void* stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mdb_unet_set_dropout": (_i, [_vp, _f, _u64]),
     "mdb_unet_backward": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
     "mdb_unet_grad_offset": (_i, [_vp, ctypes.c_char_p, ctypes.POINTER(_ll)]),
+    "mdb_unet_debug_stats": (_i, [_vp, _vp, _ll, ctypes.POINTER(_ll)]),
     "mdb_unet_train_info": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_i), ctypes.POINTER(_ll)]),
     "mdb_unet_profile_backward": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.c_char_p, _i, ctypes.POINTER(_f), _i, ctypes.POINTER(_i)]),
     "mdb_fingerprint": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -138,6 +138,17 @@ int mdb_unet_grad_offset(mdb_unet* n, const char* name, long long* off) {
   MDB_API_END
 }
 
+int mdb_unet_debug_stats(mdb_unet* n, long long* host_out, long long capacity, long long* count) {
+  MDB_API_BEGIN
+  const long long c = (long long)n->net->stats_count();
+  if (count) *count = c;
+  if (host_out) {
+    if (capacity < c) throw std::runtime_error("mdb: stats buffer too small");
+    MDB_CUDA_CHECK(cudaMemcpy(host_out, n->net->stats_ptr(), (size_t)c * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  MDB_API_END
+}
+
 int mdb_unet_train_info(mdb_unet* n, double* bwd_flops, int* nsteps, long long* numel) {
   MDB_API_BEGIN
   if (bwd_flops) *bwd_flops = n->net->bwd_flops_per_sample();

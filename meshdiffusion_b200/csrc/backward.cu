@@ -1,5 +1,6 @@
 // Bandwidth-bound kernels of the training backward pass (bf16 activations, fp32 parameter gradients).
 #include "backward.cuh"
+#include "gn_stats.cuh"
 #include <stdexcept>
 #include <string>
 
@@ -57,14 +58,13 @@ __device__ __forceinline__ void gn_stats_of(const GnBwdArgs& a, int b, int c, fl
     const int g = (c + j) / cpg;
     if (g != cur_g) {
       cur_g = g;
-      long long s1 = 0, s2 = 0;
+      StatAcc acc;
       for (int i = 0; i < cpg; ++i) {
         const int cc = g * cpg + i;
-        const long long* q = (cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * 2 : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * 2;
-        s1 += q[0]; s2 += q[1];
+        acc.add((cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * kStatWords : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * kStatWords);
       }
-      const double mm = (double)s1 * (1.0 / 16777216.0) / n;
-      double var = (double)s2 * (1.0 / 16777216.0) / n - mm * mm;
+      const double mm = acc.sum() / n;
+      double var = acc.sumsq() / n - mm * mm;
       if (var < 0) var = 0;
       m = (float)mm;
       r = (float)(1.0 / sqrt(var + (double)a.eps));
@@ -375,15 +375,14 @@ __global__ void gn_consts_kernel(GnBwdArgs a, float4* __restrict__ out, int B) {
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
   const int cpg = C / a.groups, g = c / cpg;
-  long long s1 = 0, s2 = 0;
+  StatAcc acc;
   for (int j = 0; j < cpg; ++j) {
     const int cc = g * cpg + j;
-    const long long* q = (cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * 2 : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * 2;
-    s1 += q[0]; s2 += q[1];
+    acc.add((cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * kStatWords : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * kStatWords);
   }
   const double n = (double)a.voxels * cpg;
-  const double mm = (double)s1 * (1.0 / 16777216.0) / n;
-  double var = (double)s2 * (1.0 / 16777216.0) / n - mm * mm;
+  const double mm = acc.sum() / n;
+  double var = acc.sumsq() / n - mm * mm;
   if (var < 0) var = 0;
   const float mean = (float)mm, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
   const float sc = rstd * a.gamma[c];

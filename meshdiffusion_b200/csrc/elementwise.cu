@@ -1,5 +1,6 @@
 #include "elementwise.cuh"
 #include "backward.cuh"
+#include "gn_stats.cuh"
 #include <curand_kernel.h>
 #include <stdexcept>
 #include <string>
@@ -44,13 +45,13 @@ __global__ void gn_finalize_kernel(GnFinalizeArgs a) {
   const int C = a.C0 + a.C1;
   const int cpg = C / a.groups;
   for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-    double s = 0, ss = 0;
+    StatAcc acc;
     for (int i = 0; i < cpg; ++i) {
       const int c = g * cpg + i;
-      const long long* p = (c < a.C0) ? a.stats0 + ((long long)b * a.C0 + c) * 2
-                                      : a.stats1 + ((long long)b * a.C1 + (c - a.C0)) * 2;
-      s += (double)p[0] * (1.0 / 16777216.0); ss += (double)p[1] * (1.0 / 16777216.0);
+      acc.add((c < a.C0) ? a.stats0 + ((long long)b * a.C0 + c) * kStatWords
+                         : a.stats1 + ((long long)b * a.C1 + (c - a.C0)) * kStatWords);
     }
+    const double s = acc.sum(), ss = acc.sumsq();
     const double n = a.count_per_channel * cpg;
     const double mean = s / n;
     double var = ss / n - mean * mean;
@@ -95,15 +96,14 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, in
       const int ch = c + j, g = ch / cpg;
       if (g != cur_g) {
         cur_g = g;
-        long long s1 = 0, s2 = 0;
+        StatAcc acc;
         for (int i = 0; i < cpg; ++i) {
           const int cc = g * cpg + i;
-          const long long* q = (cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * 2
-                                           : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * 2;
-          s1 += q[0]; s2 += q[1];
+          acc.add((cc < a.C0) ? a.stats0 + ((long long)b * a.C0 + cc) * kStatWords
+                              : a.stats1 + ((long long)b * a.C1 + (cc - a.C0)) * kStatWords);
         }
-        const double m = (double)s1 * (1.0 / 16777216.0) / n;
-        double var = (double)s2 * (1.0 / 16777216.0) / n - m * m;
+        const double m = acc.sum() / n;
+        double var = acc.sumsq() / n - m * m;
         if (var < 0) var = 0;
         mean = (float)m;
         rstd = (float)(1.0 / sqrt(var + (double)a.eps));
@@ -519,9 +519,9 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(SplitReduceArgs a, in
       else ((__nv_bfloat16*)a.out)[idx] = __float2bfloat16(acc);
     }
     if (a.stats) {
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.stats) + ((long long)b * a.N + n) * 2;
-      atomicAdd(dst, (unsigned long long)__double2ll_rn((double)s1 * 16777216.0));
-      atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)s2 * 16777216.0));
+      long long* dst = a.stats + ((long long)b * a.N + n) * kStatWords;
+      stat_add(dst, s1);
+      stat_add(dst + 2, s2);
     }
   }
 }

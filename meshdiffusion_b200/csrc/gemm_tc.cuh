@@ -18,6 +18,7 @@
 // Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer, w2 = TMEM allocator, w4..7 = epilogue.
 #pragma once
 #include "ptx.cuh"
+#include "gn_stats.cuh"
 
 namespace mdb {
 
@@ -92,7 +93,7 @@ struct GemmParams {
   long long rsx, rsy, rsz, rsb;
   int res_fp32;
   float alpha;
-  long long* stats;  // [Bn][N][2] (sum, sumsq) in 2^-24 fixed point (order-independent accumulation) or null
+  long long* stats;  // [Bn][N][kStatWords] (sum, sum of squares) as split fixed-point integers (gn_stats.cuh) or null
   // ---- GroupNorm-backward fusion (GNB instantiations; training data gradients). The accumulator is dL/da of a
   // GroupNorm(+SiLU)(+dropout) output a = drop(act(gamma*xhat+beta)); `res` holds the GroupNorm INPUT x (columns
   // >= res_c0 come from res1: the second source of a channel concatenation). The epilogue stores
@@ -677,9 +678,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               ts += s_part[(w * 2 + 0) * BLOCK_N + c];
               tq += s_part[(w * 2 + 1) * BLOCK_N + c];
             }
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.stats) + (static_cast<long long>(bgl) * p.N + n) * 2;
-            atomicAdd(dst, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(ts) * 16777216.0)));
-            atomicAdd(dst + 1, static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(tq) * 16777216.0)));
+            long long* dst = p.stats + (static_cast<long long>(bgl) * p.N + n) * kStatWords;
+            stat_add(dst, ts);
+            stat_add(dst + 2, tq);
           }
         }
       }

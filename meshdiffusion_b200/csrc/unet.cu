@@ -89,7 +89,7 @@ TensP UNet::new_act(int C, int R, bool stats) {
   t->off = arena_.alloc(t->bytes);
   t->ptr = dry_ ? nullptr : arena_base_ + t->off;
   if (stats) {
-    const size_t n = (size_t)cfg_.max_batch * C * 2;
+    const size_t n = (size_t)cfg_.max_batch * C * kStatWords;
     t->stats = dry_ ? nullptr : stats_base_ + stats_cursor_;
     stats_cursor_ += n;
   }

@@ -97,6 +97,9 @@ class UNet {
   long long grad_offset(const std::string& name) const;
   long long total_param_numel() const;
   int num_bwd_steps() const { return (int)bwd_steps_.size(); }
+  // diagnostics: raw GroupNorm statistics of the last forward ([tensor][B][C][2] int64, 2^-24 fixed point)
+  size_t stats_count() const { return stats_doubles_; }
+  const long long* stats_ptr() const { return stats_base_; }
   double bwd_flops_per_sample() const { return bwd_flops_ / cfg_.max_batch; }
   std::vector<std::pair<std::string, float>> profile_backward(const float* dout, float* grads, int B, cudaStream_t s);
   double flops_per_sample() const { return flops_ / cfg_.max_batch; }

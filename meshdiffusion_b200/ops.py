@@ -7,6 +7,20 @@ import torch
 from . import _native
 
 PRECISIONS = {"bf16": 0, "tf32": 1}
+STAT_WORDS = 4  # csrc/gn_stats.cuh: (sum lo, sum hi, sumsq lo, sumsq hi); value = lo * 2^-24 + hi * 2^16
+
+
+def stats_to_words(stats):
+    """float64 [B,C,2] (sum, sum of squares) -> the library's int64 [B,C,4] split fixed-point record."""
+    v = stats.double()
+    hi = torch.round(v / 65536.0)
+    lo = torch.round((v - hi * 65536.0) * 16777216.0)
+    return torch.stack([lo[..., 0], hi[..., 0], lo[..., 1], hi[..., 1]], dim=-1).to(torch.int64).contiguous()
+
+
+def words_to_stats(words):
+    w = words.double()
+    return torch.stack([w[..., 0] / 16777216.0 + w[..., 1] * 65536.0, w[..., 2] / 16777216.0 + w[..., 3] * 65536.0], dim=-1)
 
 
 def _act_dtype(precision):
@@ -33,7 +47,7 @@ def conv3d(x, weight, bias=None, stride=1, rowbias=None, residual=None, want_sta
     Cout, k = weight.shape[0], weight.shape[2]
     w = weight.detach().float().contiguous()
     y = torch.empty((B, Z // stride, Y // stride, X // stride, Cout), device=x.device, dtype=x.dtype)
-    stats = torch.zeros((B, Cout, 2), device=x.device, dtype=torch.int64) if want_stats else None
+    stats = torch.zeros((B, Cout, STAT_WORDS), device=x.device, dtype=torch.int64) if want_stats else None
     b = bias.detach().float().contiguous() if bias is not None else None
     rb = rowbias.detach().float().contiguous() if rowbias is not None else None
     if residual is not None:
@@ -41,8 +55,8 @@ def conv3d(x, weight, bias=None, stride=1, rowbias=None, residual=None, want_sta
     _native.check(L.mdb_conv3d(_native.ptr(x), B, Cin, Z, Y, X, _native.ptr(w), _native.ptr(b), Cout, k, stride,
                                _native.ptr(y), _native.ptr(rb), _native.ptr(residual), _native.ptr(stats),
                                PRECISIONS[precision], _native.current_stream()))
-    # statistics are 2^-24 fixed-point integers inside the library; return them as float64 sums
-    return (y, stats.double() / 16777216.0) if want_stats else y
+    # statistics are split fixed-point integers inside the library; return them as float64 (sum, sum of squares)
+    return (y, words_to_stats(stats)) if want_stats else y
 
 
 def groupnorm_act(x, stats, gamma, beta, silu=True, precision="bf16"):
@@ -51,7 +65,7 @@ def groupnorm_act(x, stats, gamma, beta, silu=True, precision="bf16"):
     B, C = x.shape[0], x.shape[-1]
     V = x.numel() // (B * C)
     y = torch.empty_like(x)
-    stats = torch.round(stats.double() * 16777216.0).to(torch.int64).contiguous()
+    stats = stats_to_words(stats)
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
     _native.check(L.mdb_groupnorm_act(_native.ptr(x), _native.ptr(stats), _native.ptr(g), _native.ptr(bt), _native.ptr(y),
@@ -90,7 +104,7 @@ def groupnorm_act_backward(x, stats, gamma, beta, da, add=None, silu=True, dropo
     L = _native.lib()
     B, C = x.shape[0], x.shape[-1]
     V = x.numel() // (B * C)
-    stats = torch.round(stats.double() * 16777216.0).to(torch.int64).contiguous()
+    stats = stats_to_words(stats)
     g = gamma.detach().float().contiguous()
     bt = beta.detach().float().contiguous()
     dx = torch.empty_like(x)

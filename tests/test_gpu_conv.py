@@ -99,3 +99,29 @@ def test_groupnorm_silu(precision):
     err = _rel(y, ref)
     print(f"gn+silu {precision}: rel err {err:.3e}")
     assert err < (2e-3 if precision == "tf32" else 1e-2)
+
+
+def test_groupnorm_statistics_survive_large_activations():
+    """Pre-normalisation activations of a few thousand (reached after a handful of optimiser steps in the full-size
+    training test, and possible in any trained checkpoint) push sum(x^2) over a 32^3 grid past 5.5e11, where a single
+    2^-24 fixed-point int64 wraps: the split (lo, hi) record must keep the statistics exact and GroupNorm correct."""
+    from meshdiffusion_b200 import ops
+    _ref_setup()
+    B, C, R = 2, 64, 32
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.randn(B, C, R, R, R, device="cuda", generator=g) * 6000.0 + 2500.0)
+    w = torch.randn(C, C, 3, 3, 3, device="cuda", generator=g) / (C * 27) ** 0.5
+    xin = ops.to_ndhwc(x, "bf16")
+    xr, wr = ops.from_ndhwc(xin), w.bfloat16().float()
+    ref = F.conv3d(xr, wr, None, padding=1)
+    y, stats = ops.conv3d(xin, w, None, want_stats=True, precision="bf16")
+    ref_stats = torch.stack([ref.double().sum(dim=(2, 3, 4)), (ref.double() ** 2).sum(dim=(2, 3, 4))], dim=-1)
+    assert ref_stats[..., 1].max().item() > 5.5e11, "the case must exceed the single-word range"
+    es = ((stats - ref_stats).abs() / ref_stats.abs().clamp_min(1.0)).max().item()
+    print(f"large-activation statistics: max sumsq {ref_stats[..., 1].max().item():.3e}, rel err {es:.3e}")
+    assert es < 1e-3
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.1
+    out = ops.from_ndhwc(ops.groupnorm_act(y, stats, gamma, beta, silu=True, precision="bf16"))
+    want = F.silu(F.group_norm(ops.from_ndhwc(y), 32, gamma, beta, eps=1e-6))
+    assert _rel(out, want) < 2e-2
