@@ -23,7 +23,7 @@ inline int kBwdPartRows(int B) { return kBwdTargetBlocks + B; }
 struct GnBwdArgs {
   const void* x0; int C0; long long ld0;   // forward input (raw), first source
   const void* x1; int C1; long long ld1;   // second (concatenated) source or null
-  const long long* stats0; const long long* stats1;  // forward statistics of the sources ([B][Ci][2] fixed point)
+  const long long* stats0; const long long* stats1;  // forward statistics of the sources ([B][Ci][kStatWords], gn_stats.cuh)
   const float* gamma; const float* beta;
   const void* da;          // [B][V][C] dense, activation dtype; OVERWRITTEN with dy by pass 1 (pass 2 reads dy from it)
   long long voxels; int silu; int groups; float eps;

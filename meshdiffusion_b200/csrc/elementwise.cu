@@ -38,7 +38,7 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 // ------------------------------------------------------------------ GroupNorm finalize
 // nn.GroupNorm(32, C, eps=1e-6) statistics (layers.py:589,652,660; ddpm_res64.py:120): biased variance over
-// (C/32) channels x voxels. Channel sums arrive from the producing GEMM's epilogue as 2^-24 fixed-point integers
+// (C/32) channels x voxels. Channel sums arrive from the producing GEMM's epilogue as split fixed-point integer pairs (gn_stats.cuh)
 // (integer atomics commute, so the statistics -- and with them the whole forward pass -- are bitwise reproducible).
 __global__ void gn_finalize_kernel(GnFinalizeArgs a) {
   const int b = blockIdx.x;

@@ -9,7 +9,7 @@
 namespace mdb {
 
 struct GnFinalizeArgs {
-  const long long* stats0; int C0;   // [B][C0][2] (sum, sumsq) in 2^-24 fixed point
+  const long long* stats0; int C0;   // [B][C0][kStatWords] split fixed-point (sum, sumsq) records (gn_stats.cuh)
   const long long* stats1; int C1;   // optional second (concatenated) source
   const float* gamma; const float* beta;
   float* scale; float* shift;     // [B][C0+C1]
@@ -24,7 +24,7 @@ struct NormActArgs {
   const float* scale; const float* shift;  // [B][C0+C1] (only when stats0 == nullptr: precomputed by gn_finalize)
   void* y;                                 // [B][V][C0+C1] dense
   long long voxels; int silu; int tf32;
-  // fused GroupNorm finalize: per-channel (sum, sumsq) of the two sources as 2^-24 fixed point, affine parameters
+  // fused GroupNorm finalize: per-channel (sum, sumsq) records of the two sources (gn_stats.cuh), affine parameters
   const long long* stats0; const long long* stats1;
   const float* gamma; const float* beta;
   int groups; float eps;
