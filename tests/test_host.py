@@ -202,3 +202,18 @@ def test_dataset_items_match_reference_golden(tmp_path):
     json.dump([os.path.join(tmp_path, "shape_9.npy")], open(meta, "w"))
     ds = ShapeNetDMTetDataset(meta, mask, aug=False, extension="npy")
     assert np.array_equal(ds[0].numpy(), gold["items"][0])
+
+
+def test_statistics_record_round_trip():
+    """The split fixed-point (lo, hi) GroupNorm statistics record (csrc/gn_stats.cuh) as the Python mirror encodes it:
+    exact round trip over 20 orders of magnitude, lo within +-2^15 * 2^24, far beyond the 5.5e11 single-word range."""
+    from meshdiffusion_b200 import ops
+    v = torch.tensor([[[0.0, 1.5], [-3.25e-5, 7.0e-6], [1234.5, 5.5e11], [-9.87e8, 4.3e12], [3.0e15, 1.0e19]]], dtype=torch.float64)
+    w = ops.stats_to_words(v)
+    assert w.dtype == torch.int64 and w.shape == (1, 5, ops.STAT_WORDS)
+    assert (w[..., 0].abs() <= 2 ** 39).all() and (w[..., 2].abs() <= 2 ** 39).all()
+    back = ops.words_to_stats(w)
+    assert torch.allclose(back, v, rtol=1e-12, atol=2 ** -25)
+    # sums of many records stay exact in integer arithmetic (what the kernels' atomics do)
+    many = ops.stats_to_words(torch.full((1, 1, 2), 40000.123, dtype=torch.float64)).repeat(1, 1000, 1).sum(dim=1, keepdim=True)
+    assert torch.allclose(ops.words_to_stats(many), torch.full((1, 1, 2), 40000.123 * 1000, dtype=torch.float64), rtol=1e-9)
