@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(GnBwdArgs a, int c
   const long long step = (long long)gridDim.x * k;
   // cp.async ring: every thread keeps kApplyDepth voxels of its own loads in flight in a private shared-memory slot
   // ring (no barriers: a thread only ever reads what it copied itself). The register-staged version of this kernel was
-  // latency-bound at ~1.9 TB/s (ncu: 7 warps stalled on long-scoreboard per issue, 25-37 % occupancy); with 3 blocks/SM
+  // latency-bound at ~3.7 TB/s (ncu: 7 warps stalled on long-scoreboard per issue, 25-37 % occupancy); with 3 blocks/SM
   // and 4 stages there are up to 190 KB of requests outstanding per SM.
   extern __shared__ uint4 ring[];  // [kApplyDepth][4 streams][256 threads]
   auto slot = [&](int stage, int stream) { return ring + ((stage * 4 + stream) * 256 + threadIdx.x); };
