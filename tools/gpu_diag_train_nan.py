@@ -17,7 +17,8 @@ names = [n for n, p in net.named_parameters() if p.requires_grad]
 opt = torch.optim.Adam(params, lr=lr)
 g = torch.Generator(device="cuda").manual_seed(4)
 data = (torch.rand(B, 4, R, R, R, device="cuda", generator=g) * 2 - 1) * mask
-for it in range(8):
+STEPS = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+for it in range(STEPS):
     labels = torch.randint(0, 1000, (B,), device="cuda", generator=g).float()
     noise = torch.randn(data.shape, device="cuda", generator=g)
     x = (0.7 * data + 0.7 * noise) * mask
