@@ -128,25 +128,28 @@ const WgradParams& WgradOp::params_for(int B) {
 }
 
 // ------------------------------------------------------------------ split reduction + scatter to the parameter layout
+// One thread per (tap, m, n): the split partials of that element are summed in split order (deterministic) and the
+// result goes to its slot of the parameter layout. (A thread per (m, n) looping over the taps left 16 K threads with
+// 432 dependent loads each: 38 us per launch, 5.6 ms per backward pass.)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(WgradReduceArgs a) {
-  const long long total = (long long)a.M * a.N;
+  const long long per_tap = (long long)a.M * a.N;
+  const long long total = per_tap * a.taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / a.N), n = (int)(i % a.N);
+    const int t = (int)(i / per_tap);
+    const long long r = i - (long long)t * per_tap;
+    const int m = (int)(r / a.N), n = (int)(r % a.N);
+    float acc = 0.f;
+    for (int s = 0; s < a.splits; ++s) acc += __ldg(a.partial + (((long long)s * a.taps + t) * a.Mp + m) * a.Np + n);
     const long long noff = a.ndiv ? (long long)(n % a.ndiv) * a.sn + (long long)(n / a.ndiv) * a.sn_hi : (long long)n * a.sn;
-    float* o = a.out + m * a.sm + noff;
-    for (int t = 0; t < a.taps; ++t) {
-      float acc = 0.f;
-      for (int s = 0; s < a.splits; ++s) acc += __ldg(a.partial + (((long long)s * a.taps + t) * a.Mp + m) * a.Np + n);
-      if (a.accumulate) acc += o[t * a.st];
-      o[t * a.st] = acc;
-    }
+    float* o = a.out + m * a.sm + noff + t * a.st;
+    *o = a.accumulate ? *o + acc : acc;
   }
 }
 
 void launch_wgrad_reduce(const WgradReduceArgs& a, cudaStream_t s) {
-  const long long total = (long long)a.M * a.N;
+  const long long total = (long long)a.M * a.N * a.taps;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
   MDB_CUDA_CHECK(cudaGetLastError());
 }
