@@ -36,7 +36,9 @@ typedef struct mdb_unet_config {
   int stem_ksize;          /* 3 = ddpm_conv3x3 (res64), 5 = ddpm_conv5x5 (res128) */
   int use_pos_bias;        /* 1: stem adds pos_layer(coords*0) = its bias (ddpm_res64.py:148) */
   int max_batch;
-  int precision;           /* 0 = bf16 operands, 1 = tf32 operands; fp32 accumulation either way */
+  int precision;           /* 0 = bf16 operands, 1 = tf32 operands, 2 = split bf16 ("bf16x3": every value is a (hi, lo)
+                              bf16 pair and every product hi*hi + hi*lo + lo*hi -- fp32-class results, the mode that
+                              meets the 1e-3 parity contract); fp32 accumulation in all three */
   int training;            /* 1 = also build the backward plan (bf16 operands only) and keep what it needs */
 } mdb_unet_config;
 
@@ -75,6 +77,14 @@ int mdb_unet_set_dropout(mdb_unet* net, float p, unsigned long long seed);
 int mdb_unet_backward(mdb_unet* net, const float* dout, float* grads, long long grads_numel, int batch, int accumulate,
                       void* stream);
 int mdb_unet_grad_offset(mdb_unet* net, const char* name, long long* offset);
+/* Data-parallel overlap (replaces the gradient gather of nn.DataParallel, lib/diffusion/models/utils.py:95): the backward
+ * plan is a fixed launch list; mdb_unet_grad_ready gives, per parameter, the number of launches after which its gradient
+ * is final (0 = never written). mdb_unet_backward_marked is mdb_unet_backward that additionally records the caller's CUDA
+ * events (cudaEvent_t as void*) on `stream` once mark_steps[j] launches (ascending) have been enqueued, so the host can
+ * all-reduce a finished range of the flat buffer on another stream while the remaining launches run. */
+int mdb_unet_grad_ready(mdb_unet* net, const char* name, int* n_launches);
+int mdb_unet_backward_marked(mdb_unet* net, const float* dout, float* grads, long long grads_numel, int batch,
+                             int accumulate, const int* mark_steps, void* const* mark_events, int n_marks, void* stream);
 /* Diagnostics: copies the raw GroupNorm statistics of the last forward to the host (split fixed-point records (sum lo, sum hi,
  * sumsq lo, sumsq hi), per tensor [B][C][4] in plan order); synchronises. count receives the number of int64 values. */
 int mdb_unet_debug_stats(mdb_unet* net, long long* host_out, long long capacity, long long* count);
@@ -93,33 +103,67 @@ int mdb_fingerprint(const void* const* ptrs_dev, const long long* numels_dev, in
  * pc_sampler (lib/diffusion/sampling.py:222-230, 469-478; lib/diffusion/models/utils.py:191-198).
  * eps = network output, x / x_mean fp32 NCDHW [B][C][V], mask [V]; noise may be NULL (then Philox(seed, offset)).
  */
+/* Replacement conditioning of pc_sampler's partial branch (`cond_gen`; lib/diffusion/sampling.py:453-467), fused into the
+ * same update kernel. After the masked predictor update, on channel `channel` only (g = grid mask, pm = partial_mask):
+ *   x_c <- (x_c (1 - pm) + partial pm) g;   s = mean_coef x_c + std z';   x_c <- (x_c (1 - pm) + s pm) g;   x_mean_c <- x_c
+ * with (mean_coef, std) = VPSDE.marginal_prob(., t_i) (sde_lib.py:210-214). partial / partial_mask point at channel
+ * `channel` of sample 0 ([V] floats); *_bstride is the element distance to the next sample (0 = one grid shared by the
+ * whole batch, the (1,1,R,R,R) tensors evaler.py:181-201 builds). noise: z' [B][V], or NULL for Philox(seed, offset + 2). */
+typedef struct mdb_sampler_cond {
+  const float* partial;
+  long long partial_bstride;
+  const float* partial_mask;
+  long long mask_bstride;
+  int channel;
+  float mean_coef, std; /* mdb_sampler_update only (mdb_sampler_run takes per-step tables) */
+  const float* noise;
+} mdb_sampler_cond;
+
+/* Philox: element e of step i draws its predictor noise from counter block (seed, subsequence e, offset); `offset` counts
+ * 32-bit outputs and a normal consumes two, so callers stepping a loop pass offset = 4 * i (mdb_sampler_run does). */
 int mdb_sampler_update(const float* eps, float* x, float* x_mean, const float* noise, const float* mask, float beta,
                        float std, long long voxels, int channels, int batch, unsigned long long seed,
-                       unsigned long long offset, void* stream);
-/* Whole predictor loop of pc_sampler's unconditional branch (sampling.py:469-478) without host round trips:
- * for i < n_steps: labels[i] -> network -> update. labels/betas/stds are HOST arrays of n_steps floats.
- * eps_buf: device scratch [B][C][V]; labels_buf: device scratch [B]. Noise is in-kernel Philox. */
+                       unsigned long long offset, const mdb_sampler_cond* cond /* nullable */, void* stream);
+/* Whole predictor loop of pc_sampler (unconditional branch sampling.py:469-478; partial branch :441-467 when `cond` is
+ * given) without host round trips: for i < n_steps: labels[i] -> network -> update [-> replacement conditioning while
+ * step0 + i < cond_until, i.e. min(freeze_iters, N - 1)]. labels/betas/stds (and cond_mean_coefs/cond_stds) are HOST
+ * arrays of n_steps floats for the global steps step0 .. step0 + n_steps - 1. eps_buf: device scratch [B][C][V];
+ * labels_buf: device scratch [B]. Noise is in-kernel Philox at offset 4 * (step0 + i). The call only enqueues work. */
 int mdb_sampler_run(mdb_unet* net, float* x, float* x_mean, const float* mask, const float* labels,
                     const float* betas, const float* stds, int n_steps, int batch, unsigned long long seed,
-                    float* eps_buf, float* labels_buf, void* stream);
+                    float* eps_buf, float* labels_buf, int step0, const mdb_sampler_cond* cond /* nullable */,
+                    const float* cond_mean_coefs, const float* cond_stds, int cond_until, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Training-step kernels (optimiser side). Replace get_ddpm_loss_fn's elementwise tail (lib/diffusion/losses.py:69-78),
  * torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (losses.py:45-50, 26-35) and
  * ExponentialMovingAverage.update (lib/diffusion/models/ema.py:43-64). Pointer tables / numels are DEVICE arrays of
- * n entries (one per parameter tensor); `scratch` is one device double.
+ * n entries (one per parameter tensor). The multi-tensor passes walk a CHUNK TABLE the host builds once: a device array of
+ * n_chunks (tensor index, chunk index) int32 pairs covering every tensor in pieces of mdb_chunk_elems() elements.
  */
-/* loss = mean_b[mean_{c,v}((pred-noise)^2 mask[v])] * V / mask_sum -> *loss_out; grad_pred (nullable) = dloss/dpred. */
+/* loss = mean_b[mean_{c,v}((pred-noise)^2 mask[v])] * V / mask_sum -> *loss_out; grad_pred (nullable) = dloss/dpred.
+ * scratch: one device double. */
 int mdb_ddpm_loss(const float* pred, const float* noise, const float* mask, double mask_sum, float* loss_out,
                   float* grad_pred, double* scratch, int batch, int channels, long long voxels, void* stream);
-/* coef = min(1, max_norm / (||g||_2 + 1e-6)) over all tensors -> *coef_out (and the norm in *total_norm_out). */
-int mdb_grad_clip_coef(const float* const* grads_dev, const long long* numels_dev, int n, float max_norm,
-                       float* coef_out, float* total_norm_out, double* scratch, void* stream);
-/* g *= *clip_coef (nullable); Adam(lr, beta1, beta2, eps, step >= 1, no weight decay); ema -= (1-decay)(ema - p). */
+/* x_t = (sqrt_ac[b] x_0 + sqrt_1mac[b] eps) * mask[v] (losses.py:63-66), fp32 NCDHW [B][C][V]; coefficient arrays [B] on
+ * the device; same rounding as the eager torch expression. */
+int mdb_ddpm_perturb(const float* x0, const float* noise, const float* mask, const float* sqrt_ac,
+                     const float* sqrt_1mac, float* out, int batch, int channels, long long voxels, void* stream);
+int mdb_chunk_elems(void);
+/* clip_grad_norm_ (losses.py:49): coef = min(1, max_norm / (||g||_2 + 1e-6)) over all tensors -> *coef_out (and the norm
+ * in *total_norm_out); the gradients themselves are NOT rescaled (mdb_adam_ema_step applies the coefficient on the fly).
+ * scratch: n_chunks device doubles (per-chunk partials, summed in a fixed order: reproducible). */
+int mdb_grad_clip_coef(const float* const* grads_dev, const long long* numels_dev, const int* chunks_dev, int n_chunks,
+                       float max_norm, float* coef_out, float* total_norm_out, double* scratch, void* stream);
+/* g *= *clip_coef (nullable); torch.optim.Adam(lr, beta1, beta2, eps, weight_decay) update number `step` >= 1 (losses.py:26-35);
+ * then, when ema_dev != NULL, ExponentialMovingAverage.update: ema -= (1 - ema_decay)(ema - p) (ema.py:43-64). One pass. */
 int mdb_adam_ema_step(float* const* params_dev, const float* const* grads_dev, float* const* exp_avg_dev,
-                      float* const* exp_avg_sq_dev, float* const* ema_dev, const long long* numels_dev, int n, float lr,
-                      float beta1, float beta2, float eps, int step, const float* clip_coef_dev, float ema_decay,
-                      void* stream);
+                      float* const* exp_avg_sq_dev, float* const* ema_dev, const long long* numels_dev,
+                      const int* chunks_dev, int n_chunks, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, const float* clip_coef_dev, float ema_decay, void* stream);
+/* ExponentialMovingAverage.update on its own (micro-steps that accumulate gradients without an optimiser step). */
+int mdb_ema_update(float* const* ema_dev, const float* const* params_dev, const long long* numels_dev,
+                   const int* chunks_dev, int n_chunks, float ema_decay, void* stream);
 
 /* Data-parallel training: mean all-reduce of the flat gradient buffer (what mdb_unet_backward filled) over the caller's
  * NCCL communicator (ncclComm_t passed as void*), in place, on `stream`; replaces nn.DataParallel's gradient gather

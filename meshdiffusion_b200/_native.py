@@ -34,6 +34,16 @@ class UNetConfigC(ctypes.Structure):
     ]
 
 
+class SamplerCondC(ctypes.Structure):
+    """mdb_sampler_cond (include/meshdiff_b200.h)."""
+    _fields_ = [
+        ("partial", ctypes.c_void_p), ("partial_bstride", ctypes.c_longlong),
+        ("partial_mask", ctypes.c_void_p), ("mask_bstride", ctypes.c_longlong),
+        ("channel", ctypes.c_int), ("mean_coef", ctypes.c_float), ("std", ctypes.c_float),
+        ("noise", ctypes.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); the symbol list is checked against the header by tests/test_abi.py
 _vp, _i, _ll, _f, _u64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_ulonglong, ctypes.c_double
 SIGNATURES = {
@@ -53,15 +63,21 @@ SIGNATURES = {
     "mdb_unet_set_dropout": (_i, [_vp, _f, _u64]),
     "mdb_unet_backward": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
     "mdb_unet_grad_offset": (_i, [_vp, ctypes.c_char_p, ctypes.POINTER(_ll)]),
+    "mdb_unet_grad_ready": (_i, [_vp, ctypes.c_char_p, ctypes.POINTER(_i)]),
+    "mdb_unet_backward_marked": (_i, [_vp, _vp, _vp, _ll, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_vp), _i, _vp]),
     "mdb_unet_debug_stats": (_i, [_vp, _vp, _ll, ctypes.POINTER(_ll)]),
     "mdb_unet_train_info": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_i), ctypes.POINTER(_ll)]),
     "mdb_unet_profile_backward": (_i, [_vp, _vp, _vp, _i, _vp, ctypes.c_char_p, _i, ctypes.POINTER(_f), _i, ctypes.POINTER(_i)]),
     "mdb_fingerprint": (_i, [_vp, _vp, _i, _vp, _vp]),
-    "mdb_sampler_update": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _u64, _u64, _vp]),
-    "mdb_sampler_run": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_f), _i, _i, _u64, _vp, _vp, _vp]),
+    "mdb_sampler_update": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _u64, _u64, ctypes.POINTER(SamplerCondC), _vp]),
+    "mdb_sampler_run": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_f), _i, _i, _u64, _vp, _vp,
+                             _i, ctypes.POINTER(SamplerCondC), ctypes.POINTER(_f), ctypes.POINTER(_f), _i, _vp]),
     "mdb_ddpm_loss": (_i, [_vp, _vp, _vp, _d, _vp, _vp, _vp, _i, _i, _ll, _vp]),
-    "mdb_grad_clip_coef": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
-    "mdb_adam_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _i, _vp, _f, _vp]),
+    "mdb_ddpm_perturb": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
+    "mdb_chunk_elems": (_i, []),
+    "mdb_grad_clip_coef": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
+    "mdb_adam_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _i, _vp, _f, _vp]),
+    "mdb_ema_update": (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp]),
     "mdb_allreduce_grads": (_i, [_vp, _vp, _ll, _i, _vp]),
     "mdb_conv3d": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "mdb_groupnorm_act": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _vp]),

@@ -132,6 +132,21 @@ int mdb_unet_backward(mdb_unet* n, const float* dout, float* grads, long long gr
   MDB_API_END
 }
 
+int mdb_unet_backward_marked(mdb_unet* n, const float* dout, float* grads, long long grads_numel, int B, int accumulate,
+                             const int* mark_steps, void* const* mark_events, int n_marks, void* stream) {
+  MDB_API_BEGIN
+  if (grads_numel != n->net->total_param_numel()) throw std::runtime_error("mdb: gradient buffer has the wrong size");
+  if (n_marks > 0 && (!mark_steps || !mark_events)) throw std::runtime_error("mdb: null mark arrays");
+  n->net->backward(dout, grads, B, accumulate != 0, (cudaStream_t)stream, mark_steps, mark_events, n_marks);
+  MDB_API_END
+}
+
+int mdb_unet_grad_ready(mdb_unet* n, const char* name, int* step) {
+  MDB_API_BEGIN
+  *step = n->net->grad_ready_step(name);
+  MDB_API_END
+}
+
 int mdb_unet_grad_offset(mdb_unet* n, const char* name, long long* off) {
   MDB_API_BEGIN
   *off = n->net->grad_offset(name);
@@ -174,13 +189,23 @@ int mdb_unet_profile_backward(mdb_unet* n, const float* dout, float* grads, int 
   MDB_API_END
 }
 
+static void set_cond(SamplerUpdateArgs& a, const mdb_sampler_cond* c, float coef, float stdv) {
+  if (!c || !c->partial) return;
+  if (!c->partial_mask) throw std::runtime_error("mdb: conditional sampling needs partial_mask");
+  if (c->channel < 0 || c->channel >= a.C) throw std::runtime_error("mdb: partial_channel out of range");
+  a.cond_partial = c->partial; a.cond_partial_bs = c->partial_bstride;
+  a.cond_pmask = c->partial_mask; a.cond_pmask_bs = c->mask_bstride;
+  a.cond_channel = c->channel; a.cond_coef = coef; a.cond_std = stdv; a.cond_noise = c->noise;
+}
+
 int mdb_sampler_update(const float* eps, float* x, float* x_mean, const float* noise, const float* mask, float beta,
                        float stdv, long long V, int C, int B, unsigned long long seed, unsigned long long offset,
-                       void* stream) {
+                       const mdb_sampler_cond* cond, void* stream) {
   MDB_API_BEGIN
   SamplerUpdateArgs a{};
   a.eps = eps; a.x = x; a.x_mean = x_mean; a.noise = noise; a.mask = mask; a.beta = beta; a.stdv = stdv;
   a.V = V; a.C = C; a.seed = seed; a.offset = offset;
+  if (cond) set_cond(a, cond, cond->mean_coef, cond->std);
   launch_sampler_update(a, B, (cudaStream_t)stream);
   MDB_API_END
 }
@@ -215,17 +240,23 @@ __global__ void fill_kernel(float* p, float v, int n) {
 
 int mdb_sampler_run(mdb_unet* n, float* x, float* x_mean, const float* mask, const float* labels, const float* betas,
                     const float* stds, int n_steps, int B, unsigned long long seed, float* eps_buf, float* labels_buf,
-                    void* stream) {
+                    int step0, const mdb_sampler_cond* cond, const float* cond_mean_coefs, const float* cond_stds,
+                    int cond_until, void* stream) {
   MDB_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
   const UNetConfig& c = n->net->cfg();
   const long long V = (long long)c.image_size * c.image_size * c.image_size;
+  if (cond && cond->partial && (!cond_mean_coefs || !cond_stds)) throw std::runtime_error("mdb: conditional run needs the marginal_prob tables");
+  if (cond && cond->noise) throw std::runtime_error("mdb: mdb_sampler_run draws its noise in-kernel (cond->noise must be NULL)");
   for (int i = 0; i < n_steps; ++i) {
     fill_kernel<<<(B + 127) / 128, 128, 0, s>>>(labels_buf, labels[i], B);
     n->net->forward(x, labels_buf, eps_buf, B, s);
     SamplerUpdateArgs a{};
     a.eps = eps_buf; a.x = x; a.x_mean = x_mean; a.noise = nullptr; a.mask = mask; a.beta = betas[i]; a.stdv = stds[i];
-    a.V = V; a.C = c.num_channels; a.seed = seed; a.offset = (unsigned long long)i;
+    // curand_normal consumes two 32-bit Philox outputs and `offset` counts single outputs: 4*i gives every step its own
+    // 128-bit counter block, so the noise of consecutive steps is independent
+    a.V = V; a.C = c.num_channels; a.seed = seed; a.offset = 4ull * (unsigned long long)(step0 + i);
+    if (cond && step0 + i < cond_until) set_cond(a, cond, cond_mean_coefs[i], cond_stds[i]);
     launch_sampler_update(a, B, s);
   }
   MDB_API_END
@@ -236,7 +267,7 @@ int mdb_conv3d(const void* x, int B, int cin, int z, int y_, int x_, const float
                int precision, void* stream) {
   MDB_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
-  const Precision pr = precision ? kTF32 : kBF16;
+  const Precision pr = precision_from_int(precision);
   const int xo = x_ / stride, yo = y_ / stride, zo = z / stride;
   GemmOp g;
   g.set_output(pr, xo, yo, zo, B, cout, out, cout, false);
@@ -259,7 +290,7 @@ int mdb_groupnorm_act(const void* x, const long long* stats, const float* gamma,
   cudaStream_t s = (cudaStream_t)stream;
   NormActArgs na{};
   na.x0 = x; na.C0 = C; na.ld0 = C; na.x1 = nullptr; na.C1 = 0; na.ld1 = 0; na.scale = nullptr; na.shift = nullptr;
-  na.y = y; na.voxels = V; na.silu = silu; na.tf32 = precision ? 1 : 0;
+  na.y = y; na.voxels = V; na.silu = silu; na.tf32 = (int)precision_from_int(precision);
   na.stats0 = stats; na.stats1 = nullptr; na.gamma = gamma; na.beta = beta; na.groups = 32; na.eps = 1e-6f;
   launch_norm_act(na, B, s);
   MDB_CUDA_CHECK(cudaStreamSynchronize(s));

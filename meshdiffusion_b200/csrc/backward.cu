@@ -348,8 +348,11 @@ void launch_gn_bwd_apply(const GnBwdArgs& a, int B, cudaStream_t s) {
   gn_launch_shape(a, cv, k);
   const int C = a.C0 + a.C1;
   const int gx = blocks_x(a.voxels, k, B, 444);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured_dev[64] = {};  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev < 64 ? dev : 63];
+  if (!configured || dev >= 63) {
     cudaFuncSetAttribute(gn_bwd_apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
     cudaFuncSetAttribute(gn_bwd_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);
     cudaFuncSetAttribute(gn_bwd_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kApplySmem);

@@ -75,8 +75,12 @@ void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s) {
 // vectors): its scale/shift live in registers, its source pointer is selected once, and the loop body is
 // load -> fma -> silu -> store with 4 voxels in flight. No div/mod or table lookups in the loop: the kernel is
 // HBM-bound instead of issue-bound.
-template <bool TF32>
+// MODE: 0 = bf16, 1 = tf32 (fp32 storage), 2 = split bf16 (X3: a channel vector is a 16-byte hi part and a 16-byte lo
+// part one logical row apart, on the input as on the output)
+template <int MODE>
 __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, int k) {
+  constexpr bool TF32 = MODE == 1;
+  constexpr bool X3 = MODE == 2;
   constexpr int VEC = TF32 ? 4 : 8;  // 16 bytes
   constexpr int UNROLL = 4;
   const int C = a.C0 + a.C1;
@@ -119,19 +123,25 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, in
     }
   }
   const int es = TF32 ? 4 : 2;
+  constexpr int PARTS = X3 ? 2 : 1;
   const bool first = c < a.C0;
-  const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 + c) * es
-                          : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 + (c - a.C0)) * es;
-  const long long src_stride = (first ? a.ld0 : a.ld1) * es;  // bytes per voxel
-  char* dst = (char*)a.y + ((long long)b * a.voxels * C + c) * es;
-  const long long dst_stride = (long long)C * es;
+  const char* src = first ? (const char*)a.x0 + ((long long)b * a.voxels * a.ld0 * PARTS + c) * es
+                          : (const char*)a.x1 + ((long long)b * a.voxels * a.ld1 * PARTS + (c - a.C0)) * es;
+  const long long src_stride = (first ? a.ld0 : a.ld1) * es * PARTS;  // bytes per voxel
+  const long long src_lo = (first ? a.ld0 : a.ld1) * es;              // X3: hi -> lo distance in bytes
+  char* dst = (char*)a.y + ((long long)b * a.voxels * C * PARTS + c) * es;
+  const long long dst_stride = (long long)C * es * PARTS;
+  const long long dst_lo = (long long)C * es;
   const long long step = (long long)gridDim.x * k;
   for (long long v0 = (long long)blockIdx.x * k + vl; v0 < a.voxels; v0 += step * UNROLL) {
-    uint4 raw[UNROLL];
+    uint4 raw[UNROLL], rawl[X3 ? UNROLL : 1];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long v = v0 + u * step;
-      if (v < a.voxels) raw[u] = __ldg((const uint4*)(src + v * src_stride));
+      if (v < a.voxels) {
+        raw[u] = __ldg((const uint4*)(src + v * src_stride));
+        if constexpr (X3) rawl[u] = __ldg((const uint4*)(src + v * src_stride + src_lo));
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -146,14 +156,19 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, in
         const __nv_bfloat162* h = (const __nv_bfloat162*)&raw[u];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+        if constexpr (X3) {
+          const __nv_bfloat162* l = (const __nv_bfloat162*)&rawl[u];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(l[j]); x[2 * j] += f.x; x[2 * j + 1] += f.y; }
+        }
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         float y = fmaf(x[j], sc[j], sh[j]);
-        if (a.silu) y = TF32 ? silu_f(y) : silu_fast(y);
+        if (a.silu) y = MODE == 0 ? silu_fast(y) : silu_f(y);
         x[j] = y;
       }
-      if (!TF32 && a.drop_thresh > 0) {
+      if (MODE == 0 && a.drop_thresh > 0) {
         const unsigned long long e4 = (unsigned long long)((((long long)b * a.voxels + v) * C + c) >> 2);
         const unsigned long long h0 = drop_hash64(a.seed, e4), h1 = drop_hash64(a.seed, e4 + 1);
 #pragma unroll
@@ -171,12 +186,22 @@ __global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
         *((uint4*)(dst + v * dst_stride)) = t;
+        if constexpr (X3) {
+          uint4 tl;
+          __nv_bfloat162* l = (__nv_bfloat162*)&tl;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            l[j] = __floats2bfloat162_rn(x[2 * j] - f.x, x[2 * j + 1] - f.y);
+          }
+          *((uint4*)(dst + v * dst_stride + dst_lo)) = tl;
+        }
       }
     }
   }
 }
 void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s) {
-  const int vec = a.tf32 ? 4 : 8;
+  const int vec = a.tf32 == 1 ? 4 : 8;
   const int C = a.C0 + a.C1;
   const int cv = C / vec;
   if (cv > 256 || cv < 1 || a.C0 % vec != 0) throw std::runtime_error("mdb: unsupported channel count in norm_act");
@@ -187,8 +212,9 @@ void launch_norm_act(const NormActArgs& a, int B, cudaStream_t s) {
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)B);
-  if (a.tf32) norm_act_kernel<true><<<grid, threads, 0, s>>>(a, cv, k);
-  else norm_act_kernel<false><<<grid, threads, 0, s>>>(a, cv, k);
+  if (a.tf32 == 1) norm_act_kernel<1><<<grid, threads, 0, s>>>(a, cv, k);
+  else if (a.tf32 == 2) norm_act_kernel<2><<<grid, threads, 0, s>>>(a, cv, k);
+  else norm_act_kernel<0><<<grid, threads, 0, s>>>(a, cv, k);
   MDB_LAUNCH_CHECK();
 }
 
@@ -217,8 +243,10 @@ void launch_upsample2x(const void* x, void* y, int B, int Z, int Y, int X, int C
 // (a warp per row, no per-element div/mod), then every thread emits 16-byte vectors of the [voxel][Kpad] operand
 // matrix (column = cin*k^3 + tap) through a per-column slab-offset table.
 constexpr int kIm2colYB = 4;
-template <bool TF32>
+template <int MODE>  // 0 bf16, 1 tf32, 2 split bf16 (row = [Kpad hi | Kpad lo])
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, void* __restrict__ a, int Cin, int R, int k, int Kpad) {
+  constexpr bool TF32 = MODE == 1;
+  constexpr bool X3 = MODE == 2;
   constexpr int VEC = TF32 ? 4 : 8;
   constexpr int YB = kIm2colYB;
   extern __shared__ float slab[];  // [Cin][k][k+YB-1][R + 2*pad]
@@ -269,7 +297,19 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
         __nv_bfloat162* h = (__nv_bfloat162*)&t;
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * Kpad + col0)) = t;
+        if constexpr (X3) {
+          uint4 tl;
+          __nv_bfloat162* l = (__nv_bfloat162*)&tl;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            l[j] = __floats2bfloat162_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+          }
+          *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * 2 * Kpad + col0)) = t;
+          *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * 2 * Kpad + Kpad + col0)) = tl;
+        } else {
+          *((uint4*)((__nv_bfloat16*)a + (row0 + xo) * Kpad + col0)) = t;
+        }
       }
     }
   }
@@ -277,22 +317,27 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 void launch_im2col(const float* x, void* a, int B, int Cin, int R, int k, int Kpad, int tf32, cudaStream_t s) {
   if (R % kIm2colYB != 0) throw std::runtime_error("mdb: im2col needs a grid size divisible by 4");
   const size_t smem = (size_t)Cin * k * (k + kIm2colYB - 1) * (R + 2 * (k / 2)) * sizeof(float) + (size_t)Kpad * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(im2col_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(im2col_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    configured = true;
+  static bool configured[64] = {};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !configured[dev]) {
+    cudaFuncSetAttribute(im2col_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(im2col_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(im2col_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (dev < 64) configured[dev] = true;
   }
   if (smem > 100 * 1024) throw std::runtime_error("mdb: im2col slab too large");
   const unsigned grid = (unsigned)(B * R * (R / kIm2colYB));
-  if (tf32) im2col_kernel<true><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
-  else im2col_kernel<false><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
+  if (tf32 == 1) im2col_kernel<1><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
+  else if (tf32 == 2) im2col_kernel<2><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
+  else im2col_kernel<0><<<grid, 256, smem, s>>>(x, a, Cin, R, k, Kpad);
   MDB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------ row softmax (layers.py:604)
-template <bool TF32>
+template <int MODE>  // 0 bf16, 1 tf32, 2 split bf16: hi parts in the first L bf16 of the row, lo parts in the next L
 __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L) {
+  constexpr bool TF32 = MODE == 1;
   __shared__ float red[32];
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     float* p = s + row * L;
@@ -325,7 +370,12 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L
       const int i = threadIdx.x + j * 256;
       if (i < L) {
         if (TF32) p[i] = round_tf32_rna(vals[j] * inv);
-        else ((__nv_bfloat16*)p)[i] = __float2bfloat16(vals[j] * inv);
+        else {
+          const float pv = vals[j] * inv;
+          const __nv_bfloat16 hb = __float2bfloat16(pv);
+          ((__nv_bfloat16*)p)[i] = hb;
+          if (MODE == 2) ((__nv_bfloat16*)p)[L + i] = __float2bfloat16(pv - __bfloat162float(hb));
+        }
       }
     }
   }
@@ -333,14 +383,15 @@ __global__ void softmax_rows_kernel(float* __restrict__ s, long long rows, int L
 void launch_softmax_rows(float* s, long long rows, int L, int tf32, cudaStream_t st) {
   if (L > 16 * 256) throw std::runtime_error("mdb: softmax row too long");
   const int grid = (int)(rows < 148LL * 16 ? rows : 148LL * 16);
-  if (tf32) softmax_rows_kernel<true><<<grid, 256, 0, st>>>(s, rows, L);
-  else softmax_rows_kernel<false><<<grid, 256, 0, st>>>(s, rows, L);
+  if (tf32 == 1) softmax_rows_kernel<1><<<grid, 256, 0, st>>>(s, rows, L);
+  else if (tf32 == 2) softmax_rows_kernel<2><<<grid, 256, 0, st>>>(s, rows, L);
+  else softmax_rows_kernel<0><<<grid, 256, 0, st>>>(s, rows, L);
   MDB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------ V transpose: out[b][c][v] = in[b][v][c0+c]
 template <typename T>
-__global__ void transpose_vc_kernel(const T* __restrict__ in, long long ld, int c0, T* __restrict__ out, int V, int C) {
+__global__ void transpose_vc_kernel(const T* __restrict__ in, long long ld, int c0, T* __restrict__ out, int V, int C, long long ldo) {
   __shared__ T tile[32][33];
   const int b = blockIdx.z;
   const int v0 = blockIdx.x * 32, cb = blockIdx.y * 32;
@@ -351,13 +402,13 @@ __global__ void transpose_vc_kernel(const T* __restrict__ in, long long ld, int 
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = cb + j, v = v0 + threadIdx.x;
-    if (v < V && c < C) out[((long long)b * C + c) * V + v] = tile[threadIdx.x][j];
+    if (v < V && c < C) out[((long long)b * C + c) * ldo + v] = tile[threadIdx.x][j];
   }
 }
 // bf16 fast path: 64x64 tiles, two elements (4 bytes) per thread on both the read and the write side, so every warp
 // moves full 128-byte rows (the 32x32 / 2-byte version touched half-used sectors in both directions)
 __global__ void __launch_bounds__(256) transpose_vc_bf16x2_kernel(const __nv_bfloat16* __restrict__ in, long long ld, int c0,
-                                                                  __nv_bfloat16* __restrict__ out, int V, int C) {
+                                                                  __nv_bfloat16* __restrict__ out, int V, int C, long long ldo) {
   __shared__ __nv_bfloat16 tile[64][66];
   const int b = blockIdx.z;
   const int v0 = blockIdx.x * 64, cb = blockIdx.y * 64;
@@ -375,21 +426,23 @@ __global__ void __launch_bounds__(256) transpose_vc_bf16x2_kernel(const __nv_bfl
     if (c < C && v + 1 < V) {
       __nv_bfloat162 t;
       t.x = tile[2 * tx][j]; t.y = tile[2 * tx + 1][j];
-      *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * C + c) * V + v) = t;
+      *reinterpret_cast<__nv_bfloat162*>(out + ((long long)b * C + c) * ldo + v) = t;
     }
   }
 }
 
-void launch_transpose_vc(const void* in, long long ld, int c0, void* out, int B, int V, int C, int tf32, cudaStream_t s) {
-  if (!tf32 && V % 64 == 0 && C % 64 == 0 && ld % 2 == 0 && c0 % 2 == 0) {
+void launch_transpose_vc(const void* in, long long ld, int c0, void* out, int B, int V, int C, int tf32, cudaStream_t s,
+                         long long ld_out) {
+  const long long ldo = ld_out ? ld_out : V;
+  if (!tf32 && V % 64 == 0 && C % 64 == 0 && ld % 2 == 0 && c0 % 2 == 0 && ldo % 2 == 0) {
     dim3 grid(V / 64, C / 64, B), block(32, 8);
-    transpose_vc_bf16x2_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C);
+    transpose_vc_bf16x2_kernel<<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C, ldo);
     MDB_LAUNCH_CHECK();
     return;
   }
   dim3 grid((V + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  if (tf32) transpose_vc_kernel<float><<<grid, block, 0, s>>>((const float*)in, ld, c0, (float*)out, V, C);
-  else transpose_vc_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C);
+  if (tf32) transpose_vc_kernel<float><<<grid, block, 0, s>>>((const float*)in, ld, c0, (float*)out, V, C, ldo);
+  else transpose_vc_kernel<__nv_bfloat16><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, ld, c0, (__nv_bfloat16*)out, V, C, ldo);
   MDB_LAUNCH_CHECK();
 }
 
@@ -497,8 +550,9 @@ void launch_tap_shift_sum(const void* P, long long ldp, int p_fp32, const float*
 // blockIdx.y = sample, blockIdx.x = chunk of voxels; thread = output channel (coalesced rows). Each thread owns a
 // channel for its chunk, so its statistics are accumulated in a fixed order (deterministic) and published with one
 // integer atomic per (block, channel).
-template <bool TF32>
+template <int MODE>  // 0 bf16, 1 tf32, 2 split bf16 (out / res rows are [N hi | N lo])
 __global__ void __launch_bounds__(256) split_reduce_kernel(SplitReduceArgs a, int vchunk) {
+  constexpr bool TF32 = MODE == 1;
   const int b = blockIdx.y;
   const long long v0 = (long long)blockIdx.x * vchunk;
   const long long v1 = v0 + vchunk < a.voxels ? v0 + vchunk : a.voxels;
@@ -512,10 +566,21 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(SplitReduceArgs a, in
       for (int sp = 0; sp < a.splits; ++sp) acc += a.partial[sp * a.split_stride + idx];
       if (a.res) {
         const long long ridx = (long long)b * a.res_batch_stride + v * a.N + n;
-        acc += TF32 ? ((const float*)a.res)[ridx] : __bfloat162float(((const __nv_bfloat16*)a.res)[ridx]);
+        if (MODE == 2) {
+          const __nv_bfloat16* rp = (const __nv_bfloat16*)a.res + 2 * ((long long)b * a.res_batch_stride + v * a.N) + n;
+          acc += __bfloat162float(rp[0]) + __bfloat162float(rp[a.N]);
+        } else {
+          acc += TF32 ? ((const float*)a.res)[ridx] : __bfloat162float(((const __nv_bfloat16*)a.res)[ridx]);
+        }
       }
       s1 += acc; s2 += acc * acc;
       if (TF32) ((float*)a.out)[idx] = round_tf32_rna(acc);
+      else if (MODE == 2) {
+        __nv_bfloat16* op = (__nv_bfloat16*)a.out + 2 * (idx - n) + n;
+        const __nv_bfloat16 hb = __float2bfloat16(acc);
+        op[0] = hb;
+        op[a.N] = __float2bfloat16(acc - __bfloat162float(hb));
+      }
       else ((__nv_bfloat16*)a.out)[idx] = __float2bfloat16(acc);
     }
     if (a.stats) {
@@ -529,8 +594,9 @@ void launch_split_reduce(const SplitReduceArgs& a, int B, cudaStream_t s) {
   const int vchunk = 8;
   dim3 grid((unsigned)((a.voxels + vchunk - 1) / vchunk), (unsigned)B);
   const int threads = a.N < 256 ? ((a.N + 31) / 32) * 32 : 256;
-  if (a.tf32) split_reduce_kernel<true><<<grid, threads, 0, s>>>(a, vchunk);
-  else split_reduce_kernel<false><<<grid, threads, 0, s>>>(a, vchunk);
+  if (a.tf32 == 1) split_reduce_kernel<1><<<grid, threads, 0, s>>>(a, vchunk);
+  else if (a.tf32 == 2) split_reduce_kernel<2><<<grid, threads, 0, s>>>(a, vchunk);
+  else split_reduce_kernel<0><<<grid, threads, 0, s>>>(a, vchunk);
   MDB_LAUNCH_CHECK();
 }
 
@@ -563,8 +629,31 @@ __global__ void sampler_update_kernel(SamplerUpdateArgs a, int B, float sqrt_1m_
       z = curand_normal(&st);
     }
     const float xn = __fadd_rn(xm, __fmul_rn(sqrt_beta, z));
-    a.x[i] = __fmul_rn(xn, m);
-    a.x_mean[i] = __fmul_rn(xm, m);
+    float xo = __fmul_rn(xn, m), xmo = __fmul_rn(xm, m);
+    if (a.cond_partial) {
+      const long long bc = i / a.V;
+      const int ch = (int)(bc % a.C);
+      if (ch == a.cond_channel) {
+        const long long b = bc / a.C;
+        const float pm = __ldg(a.cond_pmask + b * a.cond_pmask_bs + v);
+        const float pv = __ldg(a.cond_partial + b * a.cond_partial_bs + v);
+        const float keep = __fsub_rn(1.f, pm);
+        const float x1 = __fmul_rn(__fadd_rn(__fmul_rn(xo, keep), __fmul_rn(pv, pm)), m);
+        float z2;
+        if (a.cond_noise) {
+          z2 = a.cond_noise[b * a.V + v];
+        } else {
+          curandStatePhilox4_32_10_t st;
+          curand_init(a.seed, (unsigned long long)i, a.offset + 2, &st);
+          z2 = curand_normal(&st);
+        }
+        const float sampled = __fadd_rn(__fmul_rn(a.cond_coef, x1), __fmul_rn(a.cond_std, z2));
+        xo = __fmul_rn(__fadd_rn(__fmul_rn(x1, keep), __fmul_rn(sampled, pm)), m);
+        xmo = xo;
+      }
+    }
+    a.x[i] = xo;
+    a.x_mean[i] = xmo;
   }
 }
 void launch_sampler_update(const SamplerUpdateArgs& a, int B, cudaStream_t s) {

@@ -23,7 +23,7 @@ struct NormActArgs {
   const void* x1; int C1; long long ld1;
   const float* scale; const float* shift;  // [B][C0+C1] (only when stats0 == nullptr: precomputed by gn_finalize)
   void* y;                                 // [B][V][C0+C1] dense
-  long long voxels; int silu; int tf32;
+  long long voxels; int silu; int tf32;  // tf32: storage mode 0 = bf16, 1 = fp32 (tf32 operands), 2 = split bf16 (hi | lo rows)
   // fused GroupNorm finalize: per-channel (sum, sumsq) records of the two sources (gn_stats.cuh), affine parameters
   const long long* stats0; const long long* stats1;
   const float* gamma; const float* beta;
@@ -44,7 +44,7 @@ void launch_softmax_rows(float* s, long long rows, int L, int tf32, cudaStream_t
 
 // out[b][c][v] = in[b][v][c0 + c]
 void launch_transpose_vc(const void* in, long long ld_in, int c0, void* out, int B, int V, int C, int tf32,
-                         cudaStream_t s);
+                         cudaStream_t s, long long ld_out = 0);
 
 // temb path (ddpm_res64.py:132-136 + layers.py:542-556,680): act(temb)[B][4nf]
 void launch_temb(const float* labels, const float* w0, const float* b0, const float* w1, const float* b1, float* out,
@@ -80,6 +80,14 @@ struct SamplerUpdateArgs {
   float beta, stdv;    // beta_t, sqrt(1-alpha_bar_t)
   long long V; int C;
   unsigned long long seed, offset;  // Philox stream for in-kernel noise
+  // replacement conditioning of pc_sampler's partial branch (sampling.py:453-467), applied to channel cond_channel after
+  // the masked predictor update when cond_partial != nullptr:
+  //   x_c <- (x_c (1-pm) + partial pm) g;  s = coef x_c + std z';  x_c <- (x_c (1-pm) + s pm) g;  x_mean_c <- x_c
+  const float* cond_partial; long long cond_partial_bs;  // channel c of sample 0, sample stride (0 = shared grid)
+  const float* cond_pmask; long long cond_pmask_bs;
+  int cond_channel;
+  float cond_coef, cond_std;     // marginal_prob(x, t_i): exp(log_mean_coeff), sqrt(1 - exp(2 log_mean_coeff))
+  const float* cond_noise;       // z' [B][V] or null (then Philox(seed, element, offset + 2))
 };
 void launch_sampler_update(const SamplerUpdateArgs& a, int B, cudaStream_t s);
 

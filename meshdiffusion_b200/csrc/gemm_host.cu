@@ -82,7 +82,7 @@ int plan_splits(int X, int Y, int Z, int B, int N, int cin_total, int taps, Prec
   const int tiles_m = ((X + g.bx - 1) / g.bx) * ((Y + g.by - 1) / g.by) * ((Z + g.bz - 1) / g.bz) * ((B + g.bb - 1) / g.bb);
   const int block_n = N <= 32 ? 32 : 128;
   const int tiles = tiles_m * ((N + block_n - 1) / block_n);
-  const int ksteps = ((cin_total + kb_elems(prec) - 1) / kb_elems(prec)) * taps;
+  const int ksteps = ((cin_total + kb_elems(prec) - 1) / kb_elems(prec)) * taps * (prec == kBF16X3 ? 3 : 1);
   if (tiles > 49 || ksteps < 48) return 1;
   int S = 148 / tiles;
   if (S > 16) S = 16;
@@ -94,7 +94,8 @@ void GemmOp::enable_splits(int S, float* scratch) {
   if (S <= 1) return;
   if (pair || p.ocs != 1 || p.out_fp32 || p.bias_on_m || p.alpha != 1.f || p.res_fp32)
     throw std::runtime_error("mdb: split-K is only wired for plain NDHWC conv outputs");
-  if (p.osx != p.N || (p.res && p.rsx != p.N)) throw std::runtime_error("mdb: split-K needs dense [B][V][N] output / residual");
+  if (p.osx != (long long)p.N * parts(prec) || (p.res && p.rsx != (long long)p.N * parts(prec)))
+    throw std::runtime_error("mdb: split-K needs dense [B][V][N] output / residual");
   splits = S;
   p.splits = S;
   p.partial = scratch;
@@ -133,6 +134,11 @@ void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N,
   p.out = out;
   p.osx = osx; p.osy = osy; p.osz = osz; p.osb = osb;
   p.out_fp32 = out_fp32 ? 1 : 0;
+  p.out_lo_off = 0;
+  if (prec == kBF16X3 && !out_fp32) {  // (hi, lo) rows: physical pitch 2x the logical one, lo parts one logical row behind
+    p.out_lo_off = osx;
+    p.osx *= 2; p.osy *= 2; p.osz *= 2; p.osb *= 2;
+  }
   {
     // TF32 operands: tensor cores truncate fp32 inputs to 10 mantissa bits; rounding the stored activations to
     // nearest instead removes that systematic bias (measured on the full res64 net: rel-L2 vs fp32 2.5e-3 -> 1.5e-3,
@@ -149,20 +155,21 @@ void GemmOp::set_output(Precision pr, int X, int Y, int Z, int B, int N, void* o
   set_output_strided(pr, X, Y, Z, B, N, out, ldc, ldc * X, ldc * X * Y, ldc * X * Y * Z, out_fp32);
 }
 
-int GemmOp::add_amap(const Act& a, int halo, int sub, int px, int py, int pz) {
+int GemmOp::add_amap(const Act& a, int halo, int sub, int px, int py, int pz, int part) {
   if (n_amaps >= kMaxAMaps) throw std::runtime_error("mdb: too many A tensor maps");
   if (halo > 0 && (geo.bz != 1 || geo.bb != 1)) throw std::runtime_error("mdb: halo needs a (bx,by,1,1) tile");
   const long long es = esize(prec);
+  const long long prow = a.row() * parts(prec);  // physical row pitch in elements
   uint64_t dims[5], strides[4];
   uint32_t box[5];
-  char* base = static_cast<char*>(a.ptr);
+  char* base = static_cast<char*>(a.ptr) + (long long)part * a.row() * es;
   if (sub == 1) {
     dims[0] = a.C; dims[1] = a.X; dims[2] = a.Y; dims[3] = a.Z; dims[4] = a.B;
-    strides[0] = a.row() * es; strides[1] = strides[0] * a.X; strides[2] = strides[1] * a.Y; strides[3] = strides[2] * a.Z;
+    strides[0] = prow * es; strides[1] = strides[0] * a.X; strides[2] = strides[1] * a.Y; strides[3] = strides[2] * a.Z;
   } else {
     dims[0] = a.C; dims[1] = (a.X - px + sub - 1) / sub; dims[2] = (a.Y - py + sub - 1) / sub;
     dims[3] = (a.Z - pz + sub - 1) / sub; dims[4] = a.B;
-    const long long sx = a.row() * es, sy = sx * a.X, sz = sy * a.Y, sb = sz * a.Z;
+    const long long sx = prow * es, sy = sx * a.X, sz = sy * a.Y, sb = sz * a.Z;
     strides[0] = sx * sub; strides[1] = sy * sub; strides[2] = sz * sub; strides[3] = sb;
     base += px * sx + py * sy + pz * sz;
   }
@@ -171,14 +178,23 @@ int GemmOp::add_amap(const Act& a, int halo, int sub, int px, int py, int pz) {
   return n_amaps++;
 }
 
+void GemmOp::add_load_x(int tm_hi, int tm_lo, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc,
+                        int wc0, int tap0, int tapj) {
+  if (prec != kBF16X3) { add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0); return; }
+  // small terms first: (A lo, W hi) and (A hi, W lo) are ~2^-9 of the leading product
+  add_load(tm_lo, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0);
+  add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 1);
+  add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0);
+}
+
 void GemmOp::add_load(int tmap, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc, int wc0,
-                      int tap0, int tapj) {
+                      int tap0, int tapj, int wpart) {
   if ((int)loads.size() >= kMaxLoads) throw std::runtime_error("mdb: load table overflow");
   if (rows > kAStageRows) throw std::runtime_error("mdb: A box exceeds the stage size");
   LoadEntry e{};
   e.tmap = (uint8_t)tmap; e.nk = (uint8_t)nk; e.rows = (uint8_t)rows; e.jrows = (uint8_t)jrows;
   e.dx = (int8_t)dx; e.dy = (int8_t)dy; e.dz = (int8_t)dz; e.wsrc = (uint8_t)wsrc;
-  e.c0 = (uint16_t)c0; e.wc0 = (uint16_t)wc0; e.tap0 = (uint8_t)tap0; e.tapj = (uint8_t)tapj;
+  e.c0 = (uint16_t)c0; e.wc0 = (uint16_t)wc0; e.tap0 = (uint8_t)tap0; e.tapj = (uint8_t)tapj; e.wpart = (uint16_t)wpart;
   loads.push_back(e);
   ksteps += nk;
 }
@@ -208,19 +224,21 @@ void GemmOp::add_conv_w(const std::vector<Act>& srcs, const WSrc& wsrc, int k, i
   int coff = 0;
   if (stride == 1) {
     const bool reuse = geo.bz == 1 && geo.bb == 1 && geo.bx * (geo.by + k - 1) <= kAStageRows && p.Y >= geo.by;
+    const bool x3 = prec == kBF16X3;
     for (auto& s : srcs) {
       const int tm = add_amap(s, reuse ? k - 1 : 0);
+      const int tl = x3 ? add_amap(s, reuse ? k - 1 : 0, 1, 0, 0, 0, 1) : tm;
       for (int c0 = 0; c0 < s.C; c0 += KB) {
         if (reuse) {
           for (int dz = 0; dz < k; ++dz)
             for (int dx = 0; dx < k; ++dx)
-              add_load(tm, k, geo.bx * (geo.by + k - 1), geo.bx, dx - pad, -pad, dz - pad, c0, ws, coff + c0,
-                       (dz * k) * k + dx, k);
+              add_load_x(tm, tl, k, geo.bx * (geo.by + k - 1), geo.bx, dx - pad, -pad, dz - pad, c0, ws, coff + c0,
+                         (dz * k) * k + dx, k);
         } else {
           for (int dz = 0; dz < k; ++dz)
             for (int dy = 0; dy < k; ++dy)
               for (int dx = 0; dx < k; ++dx)
-                add_load(tm, 1, kBlockM, 0, dx - pad, dy - pad, dz - pad, c0, ws, coff + c0, (dz * k + dy) * k + dx, 0);
+                add_load_x(tm, tl, 1, kBlockM, 0, dx - pad, dy - pad, dz - pad, c0, ws, coff + c0, (dz * k + dy) * k + dx, 0);
         }
       }
       coff += s.C;
@@ -229,15 +247,17 @@ void GemmOp::add_conv_w(const std::vector<Act>& srcs, const WSrc& wsrc, int k, i
     // layers.py:626-643: pad one voxel on the high side only, then stride-2 VALID conv: in = 2*o + d.
     // Tap d reads the parity-(d&1) sub-grid at coordinate o + (d>>1); coordinate == sub-grid size -> zero fill = pad.
     if (k != 3) throw std::runtime_error("mdb: stride-2 conv supports k=3 only");
+    const bool x3 = prec == kBF16X3;
     for (auto& s : srcs) {
-      int tm[8];
+      int tm[8], tl[8];
       for (int par = 0; par < 8; ++par) tm[par] = add_amap(s, 0, 2, par & 1, (par >> 1) & 1, (par >> 2) & 1);
+      for (int par = 0; par < 8; ++par) tl[par] = x3 ? add_amap(s, 0, 2, par & 1, (par >> 1) & 1, (par >> 2) & 1, 1) : tm[par];
       for (int c0 = 0; c0 < s.C; c0 += KB)
         for (int dz = 0; dz < 3; ++dz)
           for (int dy = 0; dy < 3; ++dy)
             for (int dx = 0; dx < 3; ++dx) {
               const int par = (dx & 1) | ((dy & 1) << 1) | ((dz & 1) << 2);
-              add_load(tm[par], 1, kBlockM, 0, dx >> 1, dy >> 1, dz >> 1, c0, ws, coff + c0, (dz * 3 + dy) * 3 + dx, 0);
+              add_load_x(tm[par], tl[par], 1, kBlockM, 0, dx >> 1, dy >> 1, dz >> 1, c0, ws, coff + c0, (dz * 3 + dy) * 3 + dx, 0);
             }
       coff += s.C;
     }
@@ -264,7 +284,8 @@ void GemmOp::add_pointwise_w(const std::vector<Act>& srcs, const WSrc* w) {
   int coff = 0;
   for (auto& s : srcs) {
     const int tm = add_amap(s, 0);
-    for (int c0 = 0; c0 < s.C; c0 += KB) add_load(tm, 1, kBlockM, 0, 0, 0, 0, c0, ws, coff + c0, 0, 0);
+    const int tl = prec == kBF16X3 ? add_amap(s, 0, 1, 0, 0, 0, 1) : tm;
+    for (int c0 = 0; c0 < s.C; c0 += KB) add_load_x(tm, tl, 1, kBlockM, 0, 0, 0, 0, c0, ws, coff + c0, 0, 0);
     coff += s.C;
   }
 }
@@ -274,6 +295,11 @@ void GemmOp::set_residual(const void* res, long long ldr, long long batch_stride
   p.batch_fastest = batch_stride == 0 ? 1 : 0;  // a residual shared by every sample: keep its slice L2-resident
   p.rsx = ldr; p.rsy = ldr * p.X; p.rsz = ldr * p.X * p.Y; p.rsb = batch_stride;
   p.res_fp32 = fp32 ? 1 : 0;
+  p.res_lo_off = 0;
+  if (prec == kBF16X3 && !fp32) {
+    p.res_lo_off = ldr;
+    p.rsx *= 2; p.rsy *= 2; p.rsz *= 2; p.rsb *= 2;
+  }
 }
 
 void GemmOp::set_gn_backward(const void* x0, long long ld0, int c0, const void* x1, long long ld1, const void* consts, int silu,
@@ -302,6 +328,13 @@ void GemmOp::set_b_activation(void* ptr, int K, int N, int batch, long long rs, 
   b_from_act = true;
   p.b_batched = 1;
   const long long es = esize(prec);
+  if (prec == kBF16X3) {
+    // rows are (hi, lo) pairs: the lo parts are addressed as K coordinates [rs, rs + K) of the same map
+    if (K % kb_elems(prec) != 0) throw std::runtime_error("mdb: X3 activation-B operands need K to be a multiple of 64");
+    b_lo_off = rs;
+    encode_bmap(ptr, (int)(rs + K), N, batch, 2 * rs * es, 2 * bs * es);
+    return;
+  }
   encode_bmap(ptr, K, N, batch, rs * es, bs * es);
 }
 
@@ -315,7 +348,8 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
-template <bool TF32>
+// TF32: 0 = bf16, 1 = tf32 (rna), 2 = split bf16 (entry.wpart selects hi = bf16(w) or lo = bf16(w - hi))
+template <int TF32>
 __global__ void pack_weights_kernel(const LoadEntry* __restrict__ loads, const int* __restrict__ ks2load,
                                     const int* __restrict__ load_ks0, PackArgs args, int N, int ksteps, int KB,
                                     void* __restrict__ out) {
@@ -338,7 +372,8 @@ __global__ void pack_weights_kernel(const LoadEntry* __restrict__ loads, const i
       const long long coff = w.cdiv ? (long long)(c % w.cdiv) * w.sc + (long long)(c / w.cdiv) * w.sc_hi : (long long)c * w.sc;
       v = w.ptr[noff + coff + tap * w.st];
     }
-    if (TF32) reinterpret_cast<float*>(out)[idx] = round_tf32(v);
+    if (TF32 == 1) reinterpret_cast<float*>(out)[idx] = round_tf32(v);
+    else if (TF32 == 2 && e.wpart) reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16(v - __bfloat162float(__float2bfloat16(v)));
     else reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16(v);
   }
 }
@@ -363,14 +398,27 @@ void GemmOp::repack(cudaStream_t stream) {
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (prec == kTF32)
-    pack_weights_kernel<true><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+    pack_weights_kernel<1><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+  else if (prec == kBF16X3)
+    pack_weights_kernel<2><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
   else
-    pack_weights_kernel<false><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
+    pack_weights_kernel<0><<<blocks, 256, 0, stream>>>(d_loads, d_ks2load, d_ks0, args, p.N, ksteps, kb_elems(prec), d_wpacked);
   MDB_CUDA_CHECK(cudaGetLastError());
 }
 
 void GemmOp::finalize(cudaStream_t stream, bool pack) {
   if (loads.empty()) throw std::runtime_error("mdb: GemmOp without loads");
+  p.b_explicit_k = 0;
+  if (b_from_act && prec == kBF16X3) {
+    // activation-B operand in the split layout: every entry names the K coordinate of its B tile itself
+    // ((A hi, B hi), (A hi, B lo), (A lo, B hi) cannot be a running column of one matrix)
+    for (auto& e : loads) {
+      const long long k0 = (long long)e.wc0 + (e.wpart ? b_lo_off : 0);
+      if (k0 > 65535) throw std::runtime_error("mdb: X3 activation-B K coordinate exceeds the table's 16 bits");
+      e.wc0 = (uint16_t)k0;
+    }
+    p.b_explicit_k = 1;
+  }
   MDB_CUDA_CHECK(cudaMalloc(&d_loads, loads.size() * sizeof(LoadEntry)));
   MDB_CUDA_CHECK(cudaMemcpyAsync(d_loads, loads.data(), loads.size() * sizeof(LoadEntry), cudaMemcpyHostToDevice, stream));
   p.loads = d_loads;
@@ -421,14 +469,16 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
-template <int BN, bool TF32, bool CG2, bool GNB = false>
+template <int BN, bool TF32, bool CG2, bool GNB = false, bool X3 = false>
 static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, TF32, CG2, GNB>;
+  static bool configured[64] = {};  // the attribute is per device
+  auto kern = gemm_tc_kernel<BN, TF32, CG2, GNB, X3>;
   constexpr int smem = GemmCfg<BN, CG2>::kSmemBytes;
-  if (!configured) {
+  int dev = 0;
+  MDB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 64 || !configured[dev]) {
     MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    if (dev < 64) configured[dev] = true;
   }
   if (CG2) {
     cudaLaunchConfig_t cfg{};
@@ -471,23 +521,34 @@ void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
     }
     return;
   }
+  const bool x3 = prec == kBF16X3;
   if (pair) {
     const int work = ((tiles_m + 1) / 2) * p.n_tiles_n;
     const int pairs = sm_count() / 2;
     const int grid = 2 * (work < pairs ? work : pairs);
-    if (tf) launch_impl<128, true, true>(p, grid, stream); else launch_impl<128, false, true>(p, grid, stream);
+    if (tf) launch_impl<128, true, true>(p, grid, stream);
+    else if (x3) launch_impl<128, false, true, false, true>(p, grid, stream);
+    else launch_impl<128, false, true>(p, grid, stream);
     return;
   }
   const int total = tiles_m * p.n_tiles_n * (p.splits > 1 ? p.splits : 1);
   int grid = total < sm_count() ? total : sm_count();
-  if (block_n == 32) { if (tf) launch_impl<32, true, false>(p, grid, stream); else launch_impl<32, false, false>(p, grid, stream); }
-  else { if (tf) launch_impl<128, true, false>(p, grid, stream); else launch_impl<128, false, false>(p, grid, stream); }
+  if (block_n == 32) {
+    if (tf) launch_impl<32, true, false>(p, grid, stream);
+    else if (x3) launch_impl<32, false, false, false, true>(p, grid, stream);
+    else launch_impl<32, false, false>(p, grid, stream);
+  } else {
+    if (tf) launch_impl<128, true, false>(p, grid, stream);
+    else if (x3) launch_impl<128, false, false, false, true>(p, grid, stream);
+    else launch_impl<128, false, false>(p, grid, stream);
+  }
   if (p.splits > 1) {
     SplitReduceArgs a{};
     a.partial = p.partial; a.split_stride = p.split_stride; a.splits = p.splits;
     a.bias = p.bias; a.rowbias = p.rowbias; a.rowbias_ld = p.rowbias_ld;
     a.res = p.res; a.res_batch_stride = p.rsb;
-    a.out = p.out; a.stats = p.stats; a.voxels = (long long)p.X * p.Y * p.Z; a.N = p.N; a.tf32 = tf ? 1 : 0;
+    a.out = p.out; a.stats = p.stats; a.voxels = (long long)p.X * p.Y * p.Z; a.N = p.N; a.tf32 = tf ? 1 : (x3 ? 2 : 0);
+    if (x3) a.res_batch_stride = p.rsb / 2;  // the reduction kernel takes logical strides
     launch_split_reduce(a, p.Bn, stream);
   }
 }

@@ -18,15 +18,25 @@ namespace mdb {
                                std::to_string(__LINE__) + " (" #expr ")");                           \
   } while (0)
 
-enum Precision { kBF16 = 0, kTF32 = 1 };
+// kBF16X3 ("split bf16"): every fp32 value v is carried as a bf16 pair hi = bf16(v), lo = bf16(v - hi) and every product
+// is evaluated as hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator (three kind::f16 MMAs per k-step; the
+// dropped lo*lo term is 2^-16 relative) -- fp32-class results (the mode that meets the 1e-3 parity contract) at
+// one third of the bf16 tensor rate. An X3 tensor with a logical row pitch of `ld` channels occupies 2*ld bf16 per
+// voxel: hi parts at [0, ld), lo parts at [ld, 2*ld). All pitches handed to GemmOp / Act stay LOGICAL.
+enum Precision { kBF16 = 0, kTF32 = 1, kBF16X3 = 2 };
 inline int esize(Precision p) { return p == kTF32 ? 4 : 2; }
 inline int kb_elems(Precision p) { return kRowBytes / esize(p); }
+inline int parts(Precision p) { return p == kBF16X3 ? 2 : 1; }
+inline Precision precision_from_int(int v) {
+  if (v < 0 || v > 2) throw std::runtime_error("mdb: precision must be 0 (bf16), 1 (tf32) or 2 (bf16x3)");
+  return static_cast<Precision>(v);
+}
 
 // A dense NDHWC activation tensor (channels innermost).
 struct Act {
   void* ptr = nullptr;
   int C = 0, X = 0, Y = 0, Z = 0, B = 0;
-  long long ld = 0;  // elements between consecutive voxels (0 = dense, i.e. C)
+  long long ld = 0;  // (logical) elements between consecutive voxels (0 = dense, i.e. C)
   long long row() const { return ld ? ld : C; }
   long long voxels() const { return 1LL * X * Y * Z; }
   long long elems() const { return voxels() * B * C; }
@@ -78,9 +88,14 @@ class GemmOp {
   void set_output_strided(Precision prec, int X, int Y, int Z, int B, int N, void* out, long long osx, long long osy,
                           long long osz, long long osb, bool out_fp32);
   // adds a 5-D A tensor map over `a` (optionally a stride-2 parity sub-grid) with a (KB, bx, by+halo, bz, bb) box.
-  int add_amap(const Act& a, int halo_rows_y, int sub_stride = 1, int px = 0, int py = 0, int pz = 0);
+  // part: 0 = the tensor itself / the hi parts of an X3 tensor, 1 = its lo parts
+  int add_amap(const Act& a, int halo_rows_y, int sub_stride = 1, int px = 0, int py = 0, int pz = 0, int part = 0);
   void add_load(int tmap, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc, int wc0, int tap0,
-                int tapj);
+                int tapj, int wpart = 0);
+  // one logical A load -> 1 table entry (bf16 / tf32) or the 3 entries of the split product (X3): (A hi, W hi),
+  // (A hi, W lo), (A lo, W hi); tm_lo is the tensor map of the lo parts
+  void add_load_x(int tm_hi, int tm_lo, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc, int wc0,
+                  int tap0, int tapj);
   int add_wsrc(const WSrc& w) { wsrcs.push_back(w); return (int)wsrcs.size() - 1; }
 
   // Dense k^3 convolution (cross-correlation, zero padding k/2, stride 1 or 2 [pad-high variant]) over the channel
@@ -95,6 +110,7 @@ class GemmOp {
   void add_pointwise_w(const std::vector<Act>& srcs, const WSrc* w);
 
   // B operand taken from a runtime activation matrix instead of packed weights: Bm[batch][N][K] (K-major).
+  // (X3: logical strides; the lo parts of a row sit row_stride_elems behind its hi parts)
   void set_b_activation(void* ptr, int K, int N, int batch, long long row_stride_elems, long long batch_stride_elems);
 
   void set_bias(const float* bias, bool on_m = false) { p.bias = bias; p.bias_on_m = on_m ? 1 : 0; }
@@ -126,6 +142,7 @@ class GemmOp {
  private:
   Geometry geo{};
   bool b_from_act = false;
+  long long b_lo_off = 0;  // X3 activation-B: K coordinate of the lo parts
   void encode_bmap(void* ptr, int K, int N, int batch, long long row_stride_bytes, long long batch_stride_bytes);
 };
 

@@ -27,7 +27,7 @@ constexpr int kRowBytes = 128;                       // bytes of K per row per k
 constexpr int kAStageRows = 160;                     // 128 + up to 32 halo rows (5-tap reuse)
 constexpr int kAStageBytes = kAStageRows * kRowBytes;  // 20480, multiple of 1024
 constexpr int kMaxLoads = 2048;
-constexpr int kMaxAMaps = 10;
+constexpr int kMaxAMaps = 16;  // X3 doubles the maps (hi + lo parts): 8 parity sub-grids x 2
 constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 
@@ -39,10 +39,11 @@ struct __align__(16) LoadEntry {
   int8_t dx, dy, dz;  // coordinate offsets added to the tile origin
   uint8_t wsrc;   // (weight packer) source weight tensor
   uint16_t c0;    // channel coordinate in the A tensor
-  uint16_t wc0;   // (weight packer) input-channel offset in the weight tensor
+  uint16_t wc0;   // (weight packer) input-channel offset in the weight tensor; with GemmParams::b_explicit_k the
+                  // K coordinate of this entry's first B tile (activation-B operands of the X3 mode)
   uint8_t tap0;   // (weight packer) tap index of k-step 0
   uint8_t tapj;   // (weight packer) tap increment per k-step
-  uint16_t pad;
+  uint16_t wpart; // (weight packer, X3) 0 = hi part bf16(w), 1 = lo part bf16(w - hi)
 };
 static_assert(sizeof(LoadEntry) == 16, "LoadEntry must be 16 bytes");
 
@@ -79,6 +80,9 @@ struct GemmParams {
   int dbg_flags;       // experiment switches (bit 0: cluster-scope release on the remote t_empty arrive)
   int batch_fastest;   // enumerate the batch axis first among M-tiles (residual shared by all samples stays in L2)
   int kb_elems;        // K elements per k-step (64 bf16 / 32 tf32)
+  int b_explicit_k;    // B tile K coordinates come from LoadEntry::wc0 instead of the running k column
+  // X3 (split bf16) epilogue: the lo parts of the output / residual rows sit this many elements behind the hi parts
+  long long out_lo_off, res_lo_off;
   // epilogue
   void* out;
   long long osx, osy, osz, osb;  // output element strides per voxel axis
@@ -220,7 +224,9 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 // per-SM L2->SMEM traffic, the shared-memory operand reads and the MMA issue count per FLOP all drop.
 // GNB: GroupNorm-backward epilogue (see GemmParams::gnb_c) -- a separate instantiation, so the inference kernels'
 // code and register allocation are untouched.
-template <int BLOCK_N, bool TF32, bool CG2, bool GNB = false>
+// X3: split-bf16 operands (see Precision::kBF16X3): the main loop is unchanged (the three partial products are extra
+// k-steps of the load table); the epilogue reads residuals and stores outputs as (hi, lo) bf16 pairs.
+template <int BLOCK_N, bool TF32, bool CG2, bool GNB = false, bool X3 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, CG2>;
   constexpr int NS = Cfg::kStages;
@@ -330,6 +336,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               for (int e = 0; e < seg.epg; ++e) {
                 const uint4 raw = e == 0 ? raw0 : raw1;
                 const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
+                if (X3 && p.b_explicit_k) kc = en.wc0;
                 tma_load_5d_cg2(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
                 for (int j = 0; j < seg.nk; ++j) {
                   tma_load_3d_cg2(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, nh, bcoord);
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
               for (int e = 0; e < seg.epg; ++e) {
                 const uint4 raw = e == 0 ? raw0 : raw1;
                 const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
+                if (X3 && p.b_explicit_k) kc = en.wc0;
                 tma_load_5d(&p.amap[en.tmap], bar, sbase + e * seg.a_stride, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
                 for (int j = 0; j < seg.nk; ++j) {
                   tma_load_3d(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, n0, bcoord);
@@ -474,6 +482,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nbp);
 #pragma unroll
           for (int i = 0; i < 4; ++i) rbuf[i] = __ldg(rp + i);
+          if constexpr (X3) {
+            const uint4* rl = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nbp + p.res_lo_off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rbuf[4 + i] = __ldg(rl + i);
+          }
         }
       };
       const int ch0 = kChunkStep == 2 ? half : 0;
@@ -504,7 +517,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         if (splits > 1) {
           // split-K: raw fp32 partial sums; bias / residual / statistics are applied by the reduction kernel
           if (valid) {
-            float* pp = p.partial + (long long)(tile % splits) * p.split_stride + ooff + nb;
+            // (X3: ooff is in physical bf16 elements, twice the logical row pitch the fp32 partials use)
+            float* pp = p.partial + (long long)(tile % splits) * p.split_stride + (X3 ? (ooff >> 1) : ooff) + nb;
             if (nb + 32 <= p.N) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
@@ -577,12 +591,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   float2 f = __bfloat1622float2(h[j]);
+                  if constexpr (X3) {
+                    const float2 l = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(&rbuf[4 + i])[j]);
+                    f.x += l.x; f.y += l.y;
+                  }
                   v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y;
                 }
               }
             } else {
               const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + roff + nb;
-              for (int i = 0; i < 32; ++i) if (nb + i < p.N) v[i] += __bfloat162float(rp[i]);
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < p.N) v[i] += __bfloat162float(rp[i]) + (X3 ? __bfloat162float(rp[i + p.res_lo_off]) : 0.f);
             }
           }
         }
@@ -610,9 +629,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
                 reinterpret_cast<uint4*>(op)[i] = t;
+                if constexpr (X3) {  // lo parts: what the bf16 rounding of the hi parts lost
+                  uint4 tl;
+                  __nv_bfloat162* l = reinterpret_cast<__nv_bfloat162*>(&tl);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h[j]);
+                    l[j] = __floats2bfloat162_rn(v[8 * i + 2 * j] - f.x, v[8 * i + 2 * j + 1] - f.y);
+                  }
+                  reinterpret_cast<uint4*>(op + p.out_lo_off)[i] = tl;
+                }
               }
             } else {
-              for (int i = 0; i < 32; ++i) if (nb + i < p.N) op[i * p.ocs] = __float2bfloat16(v[i]);
+              for (int i = 0; i < 32; ++i)
+                if (nb + i < p.N) {
+                  const __nv_bfloat16 hb = __float2bfloat16(v[i]);
+                  op[i * p.ocs] = hb;
+                  if constexpr (X3) op[i * p.ocs + p.out_lo_off] = __float2bfloat16(v[i] - __bfloat162float(hb));
+                }
             }
           }
         }

@@ -85,7 +85,7 @@ float* UNet::P(const std::string& name, std::vector<long long> shape, float* ext
 TensP UNet::new_act(int C, int R, bool stats) {
   auto t = std::make_shared<Tens>();
   t->C = C; t->R = R;
-  t->bytes = (size_t)cfg_.max_batch * R * R * R * C * esize(prec_);
+  t->bytes = (size_t)cfg_.max_batch * R * R * R * C * esize(prec_) * parts(prec_);
   t->off = arena_.alloc(t->bytes);
   t->ptr = dry_ ? nullptr : arena_base_ + t->off;
   if (stats) {
@@ -152,7 +152,7 @@ TensP UNet::gn(const std::string& pname, const std::vector<TensP>& ins, bool sil
   na.x0 = ins[0]->ptr; na.C0 = ins[0]->C; na.ld0 = ins[0]->C;
   na.x1 = ins.size() > 1 ? ins[1]->ptr : nullptr; na.C1 = ins.size() > 1 ? ins[1]->C : 0; na.ld1 = na.C1;
   na.scale = nullptr; na.shift = nullptr; na.y = y->ptr; na.voxels = (long long)R * R * R; na.silu = silu ? 1 : 0;
-  na.tf32 = prec_ == kTF32;
+  na.tf32 = (int)prec_;
   na.stats0 = ins[0]->stats; na.stats1 = ins.size() > 1 ? ins[1]->stats : nullptr;
   na.gamma = gamma; na.beta = beta; na.groups = 32; na.eps = 1e-6f;
   if (train_ && drop_layer >= 0) {
@@ -266,6 +266,13 @@ TensP UNet::attn(const TensP& x, int midx) {
   TensP vT = new_act(C, R, false);
   if (!dry_) {
     const void* src = qkv->ptr; void* dst = vT->ptr; const int tf = prec_ == kTF32;
+    if (prec_ == kBF16X3) {
+      // qkv rows are [3C hi | 3C lo]; v^T rows become [V hi | V lo]
+      add_step("attn" + std::to_string(midx) + ".vT", [=](cudaStream_t s, int B) {
+        launch_transpose_vc(src, 6 * C, 2 * C, dst, B, V, C, 0, s, 2 * V);
+        launch_transpose_vc(src, 6 * C, 5 * C, (__nv_bfloat16*)dst + V, B, V, C, 0, s, 2 * V);
+      });
+    } else
     add_step("attn" + std::to_string(midx) + ".vT", [=](cudaStream_t s, int B) { launch_transpose_vc(src, 3 * C, 2 * C, dst, B, V, C, tf, s); });
   }
   // logits S[b][q][k] in fp32
@@ -283,11 +290,11 @@ TensP UNet::attn(const TensP& x, int midx) {
     g->set_alpha(1.0f / std::sqrt((float)C));
     g->finalize(0, false);
     add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
-    float* sp = (float*)S->ptr; const int tf = prec_ == kTF32;
+    float* sp = (float*)S->ptr; const int tf = (int)prec_;
     add_step("attn" + std::to_string(midx) + ".softmax", [=](cudaStream_t s, int B) { launch_softmax_rows(sp, (long long)B * V, V, tf, s); });
     GemmOp* g2 = new_gemm("attn" + std::to_string(midx) + ".pv");
     g2->set_output_strided(prec_, V, 1, 1, mb, C, O->ptr, C, 0, 0, (long long)V * C, false);
-    Act pa; pa.ptr = S->ptr; pa.C = V; pa.ld = (prec_ == kTF32) ? V : 2 * V; pa.X = V; pa.Y = 1; pa.Z = 1; pa.B = mb;
+    Act pa; pa.ptr = S->ptr; pa.C = V; pa.ld = (prec_ == kBF16) ? 2 * V : V; pa.X = V; pa.Y = 1; pa.Z = 1; pa.B = mb;
     g2->add_pointwise({pa}, nullptr, true);
     g2->set_b_activation(vT->ptr, V, C, mb, V, (long long)C * V);
     g2->finalize(0, false);
@@ -342,7 +349,8 @@ TensP UNet::upsample(const TensP& x, int midx) {
   TensP up = new_act(C, R, false);
   if (!dry_) {
     const void* src = x->ptr; void* dst = up->ptr; const int r = x->R; const int tf = prec_ == kTF32;
-    add_step("up" + std::to_string(midx) + ".nearest", [=](cudaStream_t s, int B) { launch_upsample2x(src, dst, B, r, r, r, C, tf, s); });
+    const int Cp = C * parts(prec_);  // X3: a row is 2C bf16 (hi | lo), copied as it is
+    add_step("up" + std::to_string(midx) + ".nearest", [=](cudaStream_t s, int B) { launch_upsample2x(src, dst, B, r, r, r, Cp, tf, s); });
   }
   TensP out = new_act(C, R, true);
   Scratch sp = split_begin(R, C, C, 27);
@@ -404,7 +412,7 @@ void UNet::build() {
   const int Kpad_m = ((T + KB - 1) / KB) * KB;
   const long long V0 = (long long)R0 * R0 * R0;
   auto A0 = std::make_shared<Tens>();
-  A0->bytes = (size_t)mb * V0 * Kpad * esize(prec_);
+  A0->bytes = (size_t)mb * V0 * Kpad * esize(prec_) * parts(prec_);
   A0->off = arena_.alloc(A0->bytes);
   A0->ptr = dry_ ? nullptr : arena_base_ + A0->off;
   TensP h0 = new_act(nf, R0, true);
@@ -412,9 +420,9 @@ void UNet::build() {
   if (!dry_) {
     // constant field (fp32 [V][nf]) computed once per commit with the same kernels
     float* field = (float*)dmalloc(V0 * nf * 4);
-    Am = dmalloc(V0 * Kpad_m * esize(prec_));
+    Am = dmalloc(V0 * Kpad_m * esize(prec_) * parts(prec_));
     float* fbias = (float*)dmalloc(nf * 4);
-    const int tf = prec_ == kTF32;
+    const int tf = (int)prec_;
     const bool use_pos = cfg_.use_pos_bias != 0;
     commit_steps_.push_back({"field.bias", [=](cudaStream_t s, int) { launch_add_vec(mbias, use_pos ? posb : nullptr, fbias, nf, s); }});
     commit_steps_.push_back({"field.im2col", [=](cudaStream_t s, int) { launch_im2col(mask, Am, 1, 1, R0, k, Kpad_m, tf, s); }});
@@ -509,7 +517,7 @@ void UNet::build() {
   // (2) a bandwidth kernel gathers out[v][co] = bias[co] + sum_tap P[v + off(tap)][tap*Cout + co].
   if (Cin == 4) {
     const int Np = ((T * Cin + 7) / 8) * 8;
-    const bool pf32 = prec_ == kTF32;
+    const bool pf32 = prec_ != kBF16;  // tf32 / split bf16: the per-tap projections stay fp32
     auto Pt = std::make_shared<Tens>();
     Pt->bytes = (size_t)mb * V0 * Np * (pf32 ? 4 : 2);
     Pt->off = arena_.alloc(Pt->bytes);
@@ -540,13 +548,18 @@ void UNet::build() {
   stats_doubles_ = stats_cursor_;
   if (train_) {
     // emit the backward plan: the emitters recorded during the forward pass, in reverse order
-    for (auto it = tape_.rbegin(); it != tape_.rend(); ++it) (*it)();
+    for (auto it = tape_.rbegin(); it != tape_.rend(); ++it) {
+      touched_.clear();
+      (*it)();
+      // every gradient this emitter writes is final once all of its launches have run
+      if (!dry_) for (auto& n : touched_) grad_ready_[n] = (int)bwd_steps_.size();
+    }
     tape_.clear();
     if (arena_.in_use() != 0) throw std::runtime_error("mdb: training plan leaked " + std::to_string(arena_.in_use()) + " arena bytes");
   }
 }
 
-UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(cfg.precision ? kTF32 : kBF16) {
+UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(precision_from_int(cfg.precision)) {
   if (cfg_.image_size % (1 << (cfg_.n_levels - 1)) != 0) throw std::runtime_error("mdb: image_size not divisible by 2^(levels-1)");
   if (cfg_.nf % 32 != 0) throw std::runtime_error("mdb: nf must be a multiple of 32 (GroupNorm(32))");
   train_ = cfg_.training != 0;

@@ -93,7 +93,12 @@ class UNet {
   // dout: fp32 NCDHW dL/d(out) of the preceding forward() (same x, labels, B). grads: flat fp32 buffer holding the
   // gradient of every parameter in table order (params()[i] at the sum of the numels before it); entries of
   // non-trainable tensors (mask, coords, pos_layer.weight) are left untouched. accumulate: += instead of =.
-  void backward(const float* dout, float* grads, int B, bool accumulate, cudaStream_t s);
+  // marks (optional): after `mark_steps[j]` backward launches have been enqueued (ascending), the CUDA event
+  // mark_events[j] is recorded on `s` -- the hook a data-parallel host uses to start all-reducing a gradient bucket while
+  // the rest of the backward pass still runs (grad_ready_step tells it after which launch a parameter's gradient is final)
+  void backward(const float* dout, float* grads, int B, bool accumulate, cudaStream_t s, const int* mark_steps = nullptr,
+                void* const* mark_events = nullptr, int n_marks = 0);
+  int grad_ready_step(const std::string& name) const;
   long long grad_offset(const std::string& name) const;
   long long total_param_numel() const;
   int num_bwd_steps() const { return (int)bwd_steps_.size(); }
@@ -157,6 +162,8 @@ class UNet {
   std::vector<std::unique_ptr<WgradOp>> wgrads_;
   double bwd_flops_ = 0;
   std::map<std::string, long long> goff_;
+  mutable std::vector<std::string> touched_;  // parameters whose gradient offset the running backward emitter asked for
+  std::map<std::string, int> grad_ready_;     // parameter -> number of backward launches after which its gradient is final
   float* rt_grads_ = nullptr; const float* rt_dout_ = nullptr; bool rt_accum_ = false;
   int rt_drop_thresh_ = 0; float rt_drop_scale_ = 1.f; unsigned long long rt_seed_ = 0;
   float* d_dense_out_ = nullptr;  // [mb][dense_total] gradient of the time-embedding projections

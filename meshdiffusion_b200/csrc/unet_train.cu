@@ -55,7 +55,13 @@ long long UNet::G(const std::string& name) const {
   if (dry_) return 0;
   auto it = goff_.find(name);
   if (it == goff_.end()) throw std::runtime_error("mdb: no gradient slot for " + name);
+  touched_.push_back(name);
   return it->second;
+}
+int UNet::grad_ready_step(const std::string& name) const {
+  if (goff_.find(name) == goff_.end()) throw std::runtime_error("mdb: unknown parameter " + name);
+  auto it = grad_ready_.find(name);
+  return it == grad_ready_.end() ? 0 : it->second;  // never written (mask, coords, pos_layer.weight): final from the start
 }
 long long UNet::grad_offset(const std::string& name) const {
   auto it = goff_.find(name);
@@ -91,12 +97,24 @@ void UNet::set_dropout(float p, unsigned long long seed) {
   rt_seed_ = seed;
 }
 
-void UNet::backward(const float* dout, float* grads, int B, bool accumulate, cudaStream_t s) {
+void UNet::backward(const float* dout, float* grads, int B, bool accumulate, cudaStream_t s, const int* mark_steps,
+                    void* const* mark_events, int n_marks) {
   if (!train_) throw std::runtime_error("mdb: backward() needs an engine created with training = 1");
   if (!committed_) throw std::runtime_error("mdb: parameters changed, call commit() before backward()");
   if (B < 1 || B > cfg_.max_batch) throw std::runtime_error("mdb: batch out of range");
+  for (int j = 1; j < n_marks; ++j)
+    if (mark_steps[j] < mark_steps[j - 1]) throw std::runtime_error("mdb: backward marks must be in ascending step order");
   rt_dout_ = dout; rt_grads_ = grads; rt_accum_ = accumulate;
-  for (auto& st : bwd_steps_) st.fn(s, B);
+  int mi = 0;
+  auto fire = [&](int done) {
+    while (mi < n_marks && mark_steps[mi] <= done) MDB_CUDA_CHECK(cudaEventRecord((cudaEvent_t)mark_events[mi++], s));
+  };
+  fire(0);
+  for (size_t i = 0; i < bwd_steps_.size(); ++i) {
+    bwd_steps_[i].fn(s, B);
+    fire((int)i + 1);
+  }
+  fire(1 << 30);
 }
 
 std::vector<std::pair<std::string, float>> UNet::profile_backward(const float* dout, float* grads, int B, cudaStream_t s) {

@@ -157,8 +157,11 @@ void launch_wgrad_reduce(const WgradReduceArgs& a, cudaStream_t s) {
 void WgradOp::launch(cudaStream_t s, int B, bool accumulate, float* out_ptr) {
   if (B < 1 || B > dy_.B) throw std::runtime_error("mdb: wgrad batch out of range");
   const WgradParams& p = params_for(B);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured_dev[64] = {};  // the attribute is per device
+  int dev = 0;
+  MDB_CUDA_CHECK(cudaGetDevice(&dev));
+  bool& configured = configured_dev[dev < 64 ? dev : 63];
+  if (!configured || dev >= 63) {
     MDB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     configured = true;
   }

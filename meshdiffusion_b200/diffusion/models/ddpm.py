@@ -18,6 +18,9 @@ from ... import _native
 from . import utils
 
 
+PRECISIONS = {"bf16": 0, "tf32": 1, "bf16x3": 2}  # include/meshdiff_b200.h: mdb_unet_config.precision
+
+
 def arch_from_config(config):
     """Structural hyper-parameters read by the reference constructors (ddpm_res64.py:46-53, ddpm_res128.py:48-55)."""
     is128 = config.model.name.startswith("ddpm_res128")
@@ -41,7 +44,7 @@ def _config_c(arch, max_batch, precision, training=False):
         c.attn_resolutions[i] = v
     c.num_channels, c.stem_ksize = arch["num_channels"], arch["stem_ksize"]
     c.use_pos_bias = 1 if arch["use_pos_bias"] else 0
-    c.max_batch, c.precision = max_batch, {"bf16": 0, "tf32": 1}[precision]
+    c.max_batch, c.precision = max_batch, PRECISIONS[precision]
     c.training = 1 if training else 0
     return c
 
@@ -103,13 +106,19 @@ class ScoreNet(nn.Module):
         super().__init__()
         self.arch = arch_from_config(config)
         self.precision = str(config.model.get("compute_dtype", "tf32")) if hasattr(config.model, "get") else "tf32"
-        if self.precision not in ("bf16", "tf32"):
-            raise ValueError("config.model.compute_dtype must be 'bf16' or 'tf32'")
+        if self.precision not in PRECISIONS:
+            raise ValueError("config.model.compute_dtype must be 'bf16', 'tf32' or 'bf16x3'")
         self.max_batch = int(config.model.get("engine_max_batch", 0) or 0) if hasattr(config.model, "get") else 0
         self.scale_by_sigma = bool(config.model.scale_by_sigma)
         self.dropout = float(config.model.get("dropout", 0.0)) if hasattr(config.model, "get") else 0.0
         self._train_handle, self._train_batch, self._train_synced = None, 0, None
         self._flat_grad, self._drop_calls, self._pending = None, 0, None
+        # data-parallel training: when True (the trainer sets it for the last micro-batch of an optimiser step) the backward
+        # pass all-reduces finished gradient buckets on a side stream while the remaining launches run
+        self.reduce_in_backward = False
+        self.grad_overlap = bool(config.model.get("grad_overlap", True)) if hasattr(config.model, "get") else True
+        self.bucket_bytes = int(config.model.get("grad_bucket_mb", 64)) << 20 if hasattr(config.model, "get") else 64 << 20
+        self._buckets, self._pending_reduce, self._side_stream = None, None, None
         # same buffer as the reference (ddpm_res64.py:44): float64 [num_scales]
         self.register_buffer("sigmas", torch.tensor(utils.get_sigmas(config)))
         self._names = []
@@ -212,6 +221,55 @@ class ScoreNet(nn.Module):
                 _native.check(L.mdb_unet_grad_offset(h, n.encode(), ctypes.byref(off)))
                 p = self._param(n)
                 self._grad_views[n] = self._flat_grad[off.value:off.value + p.numel()].view(p.shape)
+        self._buckets = None
+
+    def _grad_buckets(self):
+        """[(ready_launches, lo, hi)] covering the flat gradient buffer from its END (the head's gradients are final first,
+        the time-embedding MLP's last) in pieces of ~bucket_bytes; a bucket is ready when every gradient in it is final."""
+        if self._buckets is not None:
+            return self._buckets
+        L = _native.lib()
+        entries = []
+        for n in self._names:
+            off, rdy = ctypes.c_longlong(), ctypes.c_int()
+            _native.check(L.mdb_unet_grad_offset(self._train_handle, n.encode(), ctypes.byref(off)))
+            _native.check(L.mdb_unet_grad_ready(self._train_handle, n.encode(), ctypes.byref(rdy)))
+            entries.append((off.value, self._param(n).numel(), rdy.value))
+        entries.sort(reverse=True)
+        buckets, hi, ready, lo = [], self._flat_grad.numel(), 0, self._flat_grad.numel()
+        for off, numel, rdy in entries:
+            lo, ready = off, max(ready, rdy)
+            if (hi - lo) * 4 >= self.bucket_bytes:
+                buckets.append((ready, lo, hi))
+                hi, ready = lo, 0
+        if hi > 0:
+            buckets.append((ready, 0, hi))
+        buckets.sort()
+        self._buckets = buckets
+        return buckets
+
+    def _backward_with_overlapped_allreduce(self, dout, B, accumulate):
+        """mdb_unet_backward_marked + one NCCL all-reduce (mean) per bucket on a side stream, each starting as soon as the
+        launches that write its gradients have retired. The optimiser's allreduce_grads() call then only waits."""
+        import torch.distributed as dist
+        L = _native.lib()
+        buckets = self._grad_buckets()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self._flat_grad.device)
+            self._events = [torch.cuda.Event() for _ in buckets]
+            for e in self._events:
+                e.record()  # materialises the cudaEvent_t handles
+        n = len(buckets)
+        steps = (ctypes.c_int * n)(*[b[0] for b in buckets])
+        handles = (ctypes.c_void_p * n)(*[e.cuda_event for e in self._events])
+        _native.check(L.mdb_unet_backward_marked(self._train_handle, _native.ptr(dout), _native.ptr(self._flat_grad), self._flat_grad.numel(),
+                                                 B, 1 if accumulate else 0, steps, handles, n, _native.current_stream()))
+        works = []
+        with torch.cuda.stream(self._side_stream):
+            for (rdy, lo, hi), ev in zip(buckets, self._events):
+                self._side_stream.wait_event(ev)
+                works.append(dist.all_reduce(self._flat_grad[lo:hi], op=dist.ReduceOp.AVG, async_op=True))
+        self._pending_reduce = works
 
     def _push_parameters(self, handle, synced):
         """set_param for every tensor whose fingerprint differs from `synced`, then commit. Returns the fingerprints."""
@@ -258,10 +316,16 @@ class ScoreNet(nn.Module):
         none = [p.grad is None for p in params]
         ours = [p.grad is not None and p.grad.data_ptr() == self._grad_views[n].data_ptr() for p, n in zip(params, self._trainable)]
         dout = dout.float().contiguous()
+        import torch.distributed as dist
+        overlap = (self.reduce_in_backward and self.grad_overlap and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                   and dist.get_backend() == "nccl")
         with torch.cuda.device(x.device):
             if all(none) or all(ours):
-                _native.check(L.mdb_unet_backward(self._train_handle, _native.ptr(dout), _native.ptr(self._flat_grad),
-                                                  self._flat_grad.numel(), B, 0 if all(none) else 1, _native.current_stream()))
+                if overlap:
+                    self._backward_with_overlapped_allreduce(dout, B, accumulate=not all(none))
+                else:
+                    _native.check(L.mdb_unet_backward(self._train_handle, _native.ptr(dout), _native.ptr(self._flat_grad),
+                                                      self._flat_grad.numel(), B, 0 if all(none) else 1, _native.current_stream()))
                 if all(none):
                     for p, n in zip(params, self._trainable):
                         p.grad = self._grad_views[n]
@@ -276,10 +340,17 @@ class ScoreNet(nn.Module):
         self._pending = None
 
     def allreduce_grads(self):
-        """Data-parallel training: ONE all-reduce (mean) of the flat gradient buffer over NCCL, replacing the reference's
-        nn.DataParallel gather (models/utils.py:95). No-op without an initialised process group."""
+        """Data-parallel training: the mean of the flat gradient buffer over the ranks (NCCL), replacing the reference's
+        nn.DataParallel gather (models/utils.py:95). When the backward pass already launched the bucketed reductions
+        (`reduce_in_backward`), this only makes the current stream wait for them; otherwise one blocking all-reduce.
+        No-op without an initialised process group."""
         import torch.distributed as dist
         if self._flat_grad is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        if self._pending_reduce is not None:
+            for w in self._pending_reduce:
+                w.wait()
+            self._pending_reduce = None
             return
         dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
         self._flat_grad.mul_(1.0 / dist.get_world_size())

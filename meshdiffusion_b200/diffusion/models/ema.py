@@ -3,7 +3,9 @@
 effective decay warms up as `min(decay, (1 + n) / (10 + n))`, the update is `shadow -= (1 - decay_n) * (shadow - p)`, and
 `state_dict()` is `{'decay', 'num_updates', 'shadow_params'}`.
 
-The update runs as three multi-tensor (foreach) launches instead of one small kernel chain per tensor (494 tensors).
+On the GPU the update is ONE native multi-tensor pass (mdb_ema_update), or no pass of its own at all when the optimiser
+folds it into the Adam kernel (train_ops.FusedAdam.step(ema=...), which is what the training step does). Shadow tensors
+that live on the CPU (checkpoint tooling) are updated with torch ops.
 """
 import torch
 
@@ -30,9 +32,16 @@ class ExponentialMovingAverage:
 
     @torch.no_grad()
     def update(self, parameters):
-        step = 1.0 - self._current_decay()
-        delta = torch._foreach_sub(self.shadow_params, _trainable(parameters))
-        torch._foreach_mul_(delta, step)
+        decay = self._current_decay()
+        params = _trainable(parameters)
+        if self.shadow_params and self.shadow_params[0].is_cuda:
+            from ... import train_ops
+            if not hasattr(self, "_tables"):
+                self._tables = train_ops._Tables()
+            train_ops.ema_update(self.shadow_params, params, decay, self._tables)
+            return
+        delta = torch._foreach_sub(self.shadow_params, params)
+        torch._foreach_mul_(delta, 1.0 - decay)
         torch._foreach_sub_(self.shadow_params, delta)
 
     def copy_to(self, parameters):

@@ -201,15 +201,51 @@ def _native_net(model):
     return inner if isinstance(inner, ScoreNet) else None
 
 
-def _fused_update(eps, x, noise, mask_flat, beta, std):
-    """x, x_mean <- ancestral update (in place on x); one kernel."""
+class _Cond:
+    """Replacement conditioning of the partial branch (sampling.py:453-467 of the reference) in the form the update kernel
+    takes it: channel `c` of `partial` / `partial_mask` (batch 1 = one grid shared by all samples, or one per sample) and
+    the per-step marginal_prob scalars, computed with the reference's torch ops so they are bit-identical."""
+
+    def __init__(self, sde, partial, partial_mask, c, timesteps, B):
+        V = partial[0, 0].numel()
+        self.c = int(c)
+        self.partial = partial[:, c].to(torch.float32).contiguous()
+        self.pmask = partial_mask[:, c].to(torch.float32).contiguous()
+        for t in (self.partial, self.pmask):
+            if t.shape[0] not in (1, B):
+                raise ValueError("partial / partial_mask must have batch 1 or the sampling batch")
+        self.pb = V if self.partial.shape[0] == B and B > 1 else 0
+        self.mb = V if self.pmask.shape[0] == B and B > 1 else 0
+        lmc = -0.25 * timesteps ** 2 * (sde.beta_1 - sde.beta_0) - 0.5 * timesteps * sde.beta_0  # sde_lib.py:211
+        self.coefs = torch.exp(lmc).cpu().tolist()
+        self.stds = torch.sqrt(1.0 - torch.exp(2.0 * lmc)).cpu().tolist()
+
+    def struct(self, i=None, noise=None):
+        s = _native.SamplerCondC()
+        s.partial, s.partial_bstride = self.partial.data_ptr(), self.pb
+        s.partial_mask, s.mask_bstride = self.pmask.data_ptr(), self.mb
+        s.channel = self.c
+        if i is not None:
+            s.mean_coef, s.std = self.coefs[i], self.stds[i]
+        s.noise = noise.data_ptr() if noise is not None else None
+        return s
+
+
+def _fused_update(eps, x, noise, mask_flat, beta, std, cond=None):
+    """x, x_mean <- ancestral update (+ replacement conditioning when `cond` is given), in place on x; one kernel."""
     L = _native.lib()
     x_mean = torch.empty_like(x)
     B, C = x.shape[0], x.shape[1]
     V = x[0, 0].numel()
     _native.check(L.mdb_sampler_update(_native.ptr(eps), _native.ptr(x), _native.ptr(x_mean), _native.ptr(noise),
-                                       _native.ptr(mask_flat), beta, std, V, C, B, 0, 0, _native.current_stream()))
+                                       _native.ptr(mask_flat), beta, std, V, C, B, 0, 0,
+                                       ctypes.byref(cond) if cond is not None else None, _native.current_stream()))
     return x, x_mean
+
+
+def _rank():
+    import os
+    return int(os.environ.get("RANK", "0"))
 
 
 def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_steps=1, probability_flow=False,
@@ -219,7 +255,8 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
 
     `max_iters` truncates the loop to its first iterations of the N-step schedule (used by the plumbing config;
     setting num_scales=10 instead would push beta above 1). `native_rng` draws the per-step noise inside the update
-    kernel (Philox keyed by element index and step) and runs the whole loop inside the library.
+    kernel (Philox keyed by seed + rank, element index and step) and runs the whole loop inside the library -- the
+    unconditional branch and the partial (`cond_gen`) branch alike.
     """
     fused = predictor is AncestralSamplingPredictor and corrector is NoneCorrector and not probability_flow
 
@@ -265,56 +302,79 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
                 net._ensure_engine(B, x.device)
                 net.sync_parameters()
                 net._frozen = True  # nobody edits the weights inside the loop: skip per-step change detection
+            try:
+                return _run(model, net, x, use_fused, partial, partial_mask, c, freeze_iters, timesteps, B, traj,
+                            betas if use_fused else None, stds if use_fused else None,
+                            labels_all if use_fused else None, mask_flat if use_fused else None)
+            finally:
+                if use_fused:
+                    net._frozen = False  # also on OOM / NativeError / KeyboardInterrupt inside the loop
 
-            def step(x, i):
-                vec_t = torch.ones(B, device=device) * timesteps[i]
-                if not use_fused:
-                    return generic_step(model, x, vec_t)
-                eps_out = model(x, vec_t * (sde.N - 1))
-                return _fused_update(eps_out, x, torch.randn_like(x), mask_flat, betas[i], stds[i])
+    def _run(model, net, x, use_fused, partial, partial_mask, c, freeze_iters, timesteps, B, traj, betas, stds,
+             labels_all, mask_flat):
+        def step(x, i, cond=None):
+            vec_t = torch.ones(B, device=device) * timesteps[i]
+            if not use_fused:
+                return generic_step(model, x, vec_t)
+            eps_out = model(x, vec_t * (sde.N - 1))
+            z = torch.randn_like(x)
+            z2 = torch.randn_like(x[:, c]).contiguous() if cond is not None else None  # same draw order as the reference
+            return _fused_update(eps_out, x, z, mask_flat, betas[i], stds[i], cond.struct(i, z2) if cond is not None else None)
 
-            if partial is not None:
-                assert partial.dim() == 5
-                vec_t = torch.ones(B, device=device) * timesteps[0]
-                x[:, c] = partial[:, c] * grid_mask[:, c]
-                pmean, pstd = sde.marginal_prob(x, vec_t)
-                # NB: (B,1,1,1,1) * (B,D,H,W) broadcasts to (B,B,D,H,W) in the reference (sampling.py:436-440)
-                sampled = pmean[:, c] + pstd[:, None, None, None, None] * torch.randn_like(pmean[:, c])
-                x[:, c] = (x[:, c] * (1 - partial_mask[:, c]) + sampled[:, c] * partial_mask[:, c]) * grid_mask[:, c]
+        if partial is not None:
+            assert partial.dim() == 5
+            vec_t = torch.ones(B, device=device) * timesteps[0]
+            x[:, c] = partial[:, c] * grid_mask[:, c]
+            pmean, pstd = sde.marginal_prob(x, vec_t)
+            # NB: (B,1,1,1,1) * (B,D,H,W) broadcasts to (B,B,D,H,W) in the reference (sampling.py:436-440)
+            sampled = pmean[:, c] + pstd[:, None, None, None, None] * torch.randn_like(pmean[:, c])
+            x[:, c] = (x[:, c] * (1 - partial_mask[:, c]) + sampled[:, c] * partial_mask[:, c]) * grid_mask[:, c]
+            x_mean = x
+            total = sde.N if max_iters is None else min(max_iters, sde.N)
+            cond_until = min(freeze_iters, sde.N - 1)
+            if use_fused:
+                # the replacement + re-noising runs inside the update kernel (one launch per step); with native_rng the
+                # whole loop runs inside the library
+                cond = _Cond(sde, partial, partial_mask, c, timesteps, B)
+                x = x.contiguous()
+                if native_rng and not return_traj:
+                    x_mean = _native_loop(net, x, mask_flat, labels_all, betas, stds, total, seed + _rank(), 0, cond, cond_until)
+                else:
+                    for i in range(total):
+                        x, x_mean = step(x, i, cond if i < cond_until else None)
+                total = 0
+            for i in range(total):
+                x, x_mean = step(x, i)
+                if i != sde.N - 1 and i < freeze_iters:
+                    keep, pm = 1 - partial_mask[:, c], partial_mask[:, c]
+                    x[:, c] = (x[:, c] * keep + partial[:, c] * pm) * grid_mask[:, c]
+                    x_mean[:, c] = (x_mean[:, c] * keep + partial[:, c] * pm) * grid_mask[:, c]
+                    vec_t = torch.ones(B, device=device) * timesteps[i]
+                    pmean, pstd = sde.marginal_prob(x, vec_t)
+                    sampled = pmean[:, c] + pstd[:, None, None, None] * torch.randn_like(pmean[:, c])
+                    x[:, c] = (x[:, c] * keep + sampled * pm) * grid_mask[:, c]
+                    x_mean[:, c] = x[:, c]
+        else:
+            total = sde.N - 1 if max_iters is None else min(max_iters, sde.N - 1)
+            if use_fused and native_rng and not return_traj:
+                x_mean = _native_loop(net, x, mask_flat, labels_all, betas, stds, total, seed + _rank())
+            else:
                 x_mean = x
-                total = sde.N if max_iters is None else min(max_iters, sde.N)
                 for i in range(total):
                     x, x_mean = step(x, i)
-                    if i != sde.N - 1 and i < freeze_iters:
-                        keep, pm = 1 - partial_mask[:, c], partial_mask[:, c]
-                        x[:, c] = (x[:, c] * keep + partial[:, c] * pm) * grid_mask[:, c]
-                        x_mean[:, c] = (x_mean[:, c] * keep + partial[:, c] * pm) * grid_mask[:, c]
-                        vec_t = torch.ones(B, device=device) * timesteps[i]
-                        pmean, pstd = sde.marginal_prob(x, vec_t)
-                        sampled = pmean[:, c] + pstd[:, None, None, None] * torch.randn_like(pmean[:, c])
-                        x[:, c] = (x[:, c] * keep + sampled * pm) * grid_mask[:, c]
-                        x_mean[:, c] = x[:, c]
-            else:
-                total = sde.N - 1 if max_iters is None else min(max_iters, sde.N - 1)
-                if use_fused and native_rng and not return_traj:
-                    x_mean = _native_loop(net, x, mask_flat, labels_all, betas, stds, total, seed)
-                else:
-                    x_mean = x
-                    for i in range(total):
-                        x, x_mean = step(x, i)
-                        if return_traj and i >= 700 and i % 10 == 0:
-                            traj.append(compute_xzero(model, x, timesteps[i], grid_mask))
-            if use_fused:
-                net._frozen = False
-            if return_traj:
-                return traj, sde.N * (n_steps + 1)
-            return inverse_scaler(x_mean if denoise else x), sde.N * (n_steps + 1)
+                    if return_traj and i >= 700 and i % 10 == 0:
+                        traj.append(compute_xzero(model, x, timesteps[i], grid_mask))
+        if return_traj:
+            return traj, sde.N * (n_steps + 1)
+        return inverse_scaler(x_mean if denoise else x), sde.N * (n_steps + 1)
 
     return pc_sampler
 
 
-def _native_loop(net, x, mask_flat, labels, betas, stds, total, seed):
-    """The whole unconditional loop inside the library (mdb_sampler_run): no Python between steps."""
+def _native_loop(net, x, mask_flat, labels, betas, stds, total, seed, step0=0, cond=None, cond_until=0):
+    """Steps step0 .. step0+total-1 of the loop inside the library (mdb_sampler_run): no Python between steps. The
+    schedule lists are indexed by the GLOBAL step; `cond` (a _Cond) switches on the partial branch's replacement
+    conditioning for the steps below `cond_until`."""
     L = _native.lib()
     B = x.shape[0]
     net._ensure_engine(B, x.device)
@@ -322,10 +382,13 @@ def _native_loop(net, x, mask_flat, labels, betas, stds, total, seed):
     x_mean = torch.empty_like(x)
     eps_buf = torch.empty_like(x)
     labels_buf = torch.empty(B, device=x.device, dtype=torch.float32)
-    arr = lambda v: (ctypes.c_float * total)(*v[:total])
+    arr = lambda v: (ctypes.c_float * total)(*v[step0:step0 + total])
+    cs = cond.struct() if cond is not None else None
     _native.check(L.mdb_sampler_run(net._handle, _native.ptr(x), _native.ptr(x_mean), _native.ptr(mask_flat), arr(labels),
                                     arr(betas), arr(stds), total, B, int(seed), _native.ptr(eps_buf),
-                                    _native.ptr(labels_buf), _native.current_stream()))
+                                    _native.ptr(labels_buf), int(step0), ctypes.byref(cs) if cs is not None else None,
+                                    arr(cond.coefs) if cond is not None else None, arr(cond.stds) if cond is not None else None,
+                                    int(cond_until), _native.current_stream()))
     return x_mean
 
 

@@ -1,12 +1,14 @@
 """Operator-level wrappers over the C ABI (used by the parity tests; the engine itself stays inside the library).
 
-Activations are NDHWC torch tensors on the GPU: bfloat16 for precision='bf16', float32 for precision='tf32'.
+Activations are NDHWC torch tensors on the GPU: bfloat16 for precision='bf16', float32 for precision='tf32', and for
+precision='bf16x3' (split bf16) bfloat16 rows of 2C entries: the hi parts bf16(v) of the C channels followed by their
+lo parts bf16(v - hi).
 """
 import torch
 
 from . import _native
 
-PRECISIONS = {"bf16": 0, "tf32": 1}
+PRECISIONS = {"bf16": 0, "tf32": 1, "bf16x3": 2}
 STAT_WORDS = 4  # csrc/gn_stats.cuh: (sum lo, sum hi, sumsq lo, sumsq hi); value = lo * 2^-24 + hi * 2^16
 
 
@@ -24,15 +26,23 @@ def words_to_stats(words):
 
 
 def _act_dtype(precision):
-    return torch.bfloat16 if precision == "bf16" else torch.float32
+    return torch.float32 if precision == "tf32" else torch.bfloat16
 
 
 def to_ndhwc(x_ncdhw, precision):
-    """[B,C,D,H,W] fp32 -> contiguous [B,D,H,W,C] in the operand dtype."""
-    return x_ncdhw.permute(0, 2, 3, 4, 1).contiguous().to(_act_dtype(precision))
+    """[B,C,D,H,W] fp32 -> contiguous [B,D,H,W,C] in the operand dtype ([B,D,H,W,2C] = hi | lo for 'bf16x3')."""
+    y = x_ncdhw.permute(0, 2, 3, 4, 1).contiguous()
+    if precision == "bf16x3":
+        hi = y.to(torch.bfloat16)
+        lo = (y.float() - hi.float()).to(torch.bfloat16)
+        return torch.cat([hi, lo], dim=-1).contiguous()
+    return y.to(_act_dtype(precision))
 
 
-def from_ndhwc(y):
+def from_ndhwc(y, precision=None):
+    if precision == "bf16x3":
+        C = y.shape[-1] // 2
+        y = y[..., :C].float() + y[..., C:].float()
     return y.float().permute(0, 4, 1, 2, 3).contiguous()
 
 
@@ -44,9 +54,12 @@ def conv3d(x, weight, bias=None, stride=1, rowbias=None, residual=None, want_sta
     L = _native.lib()
     assert x.is_cuda and x.is_contiguous() and x.dtype == _act_dtype(precision)
     B, Z, Y, X, Cin = x.shape
+    parts = 2 if precision == "bf16x3" else 1
+    Cin //= parts
     Cout, k = weight.shape[0], weight.shape[2]
+    assert weight.shape[1] == Cin
     w = weight.detach().float().contiguous()
-    y = torch.empty((B, Z // stride, Y // stride, X // stride, Cout), device=x.device, dtype=x.dtype)
+    y = torch.empty((B, Z // stride, Y // stride, X // stride, Cout * parts), device=x.device, dtype=x.dtype)
     stats = torch.zeros((B, Cout, STAT_WORDS), device=x.device, dtype=torch.int64) if want_stats else None
     b = bias.detach().float().contiguous() if bias is not None else None
     rb = rowbias.detach().float().contiguous() if rowbias is not None else None
@@ -64,6 +77,8 @@ def groupnorm_act(x, stats, gamma, beta, silu=True, precision="bf16"):
     L = _native.lib()
     B, C = x.shape[0], x.shape[-1]
     V = x.numel() // (B * C)
+    if precision == "bf16x3":
+        C //= 2
     y = torch.empty_like(x)
     stats = stats_to_words(stats)
     g = gamma.detach().float().contiguous()
@@ -80,7 +95,7 @@ def sampler_update(eps, x, noise, mask, beta, std, seed=0, offset=0):
     V = x[0, 0].numel()
     x_mean = torch.empty_like(x)
     _native.check(L.mdb_sampler_update(_native.ptr(eps), _native.ptr(x), _native.ptr(x_mean), _native.ptr(noise),
-                                       _native.ptr(mask), float(beta), float(std), V, C, B, seed, offset,
+                                       _native.ptr(mask), float(beta), float(std), V, C, B, seed, offset, None,
                                        _native.current_stream()))
     return x, x_mean
 

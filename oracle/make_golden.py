@@ -301,6 +301,7 @@ def golden_marching_tets():
         cases[case + "_uvs_tail"] = r[2][-64:]
         cases[case + "_uvs_sum"] = np.array([r[2].astype(np.float64).sum()])
     np.savez_compressed(os.path.join(GOLD, "marching_tets_64.npz"), **cases)
+    golden_marching_tets_128(mt)
     # grid mask derivable from the tet grid (data/get_tet_mask.py): check against the shipped mask
     coords = mt_oracle.grid_coords_of_tet_vertices(verts)
     mask = np.zeros((64, 64, 64), np.float32)
@@ -308,6 +309,50 @@ def golden_marching_tets():
     ref_mask = torch.load(os.path.join(REF, "data/grid_mask_64.pt"), map_location="cpu").numpy()
     assert np.array_equal(mask, ref_mask), "grid mask derived from the tet grid differs from data/grid_mask_64.pt"
     print("grid_mask_64 == scatter of tet vertices:", int(mask.sum()), "voxels")
+
+
+def int_digest(a):
+    """sha256 of an integer array as little-endian int64 -- pins every entry without storing 10^5 of them."""
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype="<i8").tobytes()).digest(), dtype=np.uint8)
+
+
+def golden_marching_tets_128(mt):
+    """R=128 tet grid (nvdiffrec/data/tets/128_tets_cropped.npz: 253 024 vertices, 1 387 746 tets): the reference DMTet's
+    integer outputs are pinned by length + sha256 digests (bit-exactness is a hash equality), the float outputs by sampled
+    entries and sums; the oracle must agree with the reference entry by entry first."""
+    tets = np.load(os.path.join(REF, "nvdiffrec/data/tets/128_tets_cropped.npz"))
+    verts, idx = tets["vertices"], tets["indices"]
+    cases = {}
+    for case, seed in (("sphere", 0), ("noisy", 1)):
+        sdf, pos = synth.synthetic_dmtet(verts, seed=seed, noisy=(case == "noisy"), res=128)
+        with torch.no_grad():
+            r = [t.numpy() for t in mt(torch.tensor(pos), torch.tensor(sdf), torch.tensor(idx).long())]
+        o = mt_oracle.marching_tets(pos, sdf, idx)
+        names = ["verts", "faces", "uvs", "uv_idx", "face_to_valid_tet", "valid_vert_idx"]
+        for n, a, b in zip(names, r, o):
+            assert a.shape == b.shape, (case, n, a.shape, b.shape)
+            if a.dtype.kind in "iu":
+                assert np.array_equal(a, b), f"marching tets 128 {case}: integer output {n} differs"
+            else:
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-7), f"marching tets 128 {case}: {n} differs"
+        print(f"marching tets 128 {case}: {r[0].shape[0]} verts, {r[1].shape[0]} faces -- oracle == reference")
+        for n, a in zip(names, r):
+            cases[f"{case}_{n}_shape"] = np.array(a.shape)
+            if a.dtype.kind in "iu":
+                cases[f"{case}_{n}_sha256"] = int_digest(a)
+            else:
+                sel = np.linspace(0, a.shape[0] - 1, 257).astype(np.int64)
+                cases[f"{case}_{n}_rows"] = sel
+                cases[f"{case}_{n}_sample"] = a[sel]
+                cases[f"{case}_{n}_sum"] = np.array([a.astype(np.float64).sum()])
+    np.savez_compressed(os.path.join(GOLD, "marching_tets_128.npz"), **cases)
+    coords = mt_oracle.grid_coords_of_tet_vertices(verts)
+    mask = np.zeros((128, 128, 128), np.float32)
+    mask[coords[:, 0], coords[:, 1], coords[:, 2]] = 1
+    ref_mask = torch.load(os.path.join(REF, "data/grid_mask_128.pt"), map_location="cpu").numpy()
+    assert np.array_equal(mask, ref_mask), "grid mask derived from the 128 tet grid differs from data/grid_mask_128.pt"
+    print("grid_mask_128 == scatter of tet vertices:", int(mask.sum()), "voxels")
 
 
 if __name__ == "__main__":

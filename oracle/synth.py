@@ -59,7 +59,7 @@ def synthetic_inputs(R, batch, seed, mask):
     return x, labels
 
 
-def synthetic_dmtet(vertices, seed, noisy):
+def synthetic_dmtet(vertices, seed, noisy, res=64):
     """sdf / vertex positions for marching-tet tests: a sphere of radius 0.3, optionally with
     sign noise (many disconnected components -> stresses the ordering rules) and random deformation."""
     rng = np.random.RandomState(seed)
@@ -73,5 +73,5 @@ def synthetic_dmtet(vertices, seed, noisy):
         sdf[rng.rand(v.shape[0]) < 0.01] = 0.0  # sign(0) = 0 is "outside" (occ = sdf > 0)
         deform = (rng.rand(*v.shape).astype(np.float32) - 0.5)
     sdf = np.sign(sdf).astype(np.float32) if noisy else sdf
-    pos = (v * np.float32(1.1) + np.float32(2 / (64 * 2)) * deform * np.float32(3.0)).astype(np.float32)
+    pos = (v * np.float32(1.1) + np.float32(2 / (res * 2)) * deform * np.float32(3.0)).astype(np.float32)
     return sdf, pos

@@ -71,3 +71,6 @@ def test_train_cli_writes_reference_checkpoint_layout(tmp_path):
     assert len(ck["ema"]["shadow_params"]) == 494
     losses = [float(l.split("training_loss:")[1]) for l in (r.stderr + r.stdout).splitlines() if "training_loss:" in l]
     assert len(losses) >= 3 and all(np.isfinite(losses))
+    # loop bounds and names of the reference trainer (trainer.py:95,128-130): steps 0..n_iters, final checkpoint_<n_iters>.pth
+    final = torch.load(os.path.join(wd, "checkpoints", "checkpoint_3.pth"), map_location="cpu", weights_only=False)
+    assert final["step"] == 4 and set(final["optimizer"]["state"][2]) == {"step", "exp_avg", "exp_avg_sq"}

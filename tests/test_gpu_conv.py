@@ -1,7 +1,8 @@
 """Parity of the tcgen05 implicit-GEMM convolution against torch's fp32 conv3d (TF32 disabled) on the same inputs.
 
 Tolerances (max |diff| / max |ref|): tf32 operands 2e-3, bf16 operands 2e-2 -- operand rounding only, the
-accumulation is fp32 in TMEM in both modes.
+accumulation is fp32 in TMEM in both modes; split bf16 ("bf16x3": hi*hi + hi*lo + lo*hi, the dropped lo*lo term is
+2^-16 of a product; the 5^3 head case sums 16 000 products per output) 1e-4.
 """
 import pytest
 import torch
@@ -9,7 +10,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"tf32": 2e-3, "bf16": 2e-2}
+TOL = {"tf32": 2e-3, "bf16": 2e-2, "bf16x3": 1e-4}
 
 
 def _ref_setup():
@@ -36,7 +37,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("case", CASES)
 def test_conv3d_matches_torch(case, precision):
     from meshdiffusion_b200 import ops
@@ -52,7 +53,7 @@ def test_conv3d_matches_torch(case, precision):
         ref = F.conv3d(F.pad(x, (0, 1, 0, 1, 0, 1)), w, b, stride=2, padding=0)
     xin = ops.to_ndhwc(x, precision)
     y, stats = ops.conv3d(xin, w, b, stride=stride, want_stats=True, precision=precision)
-    out = ops.from_ndhwc(y)
+    out = ops.from_ndhwc(y, precision)
     assert out.shape == ref.shape
     err = _rel(out, ref)
     print(f"conv {case} {precision}: rel err {err:.3e}")
@@ -64,7 +65,7 @@ def test_conv3d_matches_torch(case, precision):
     assert _rel(stats[..., 1], q_ref) < TOL[precision]
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "bf16x3"])
 def test_conv3d_epilogue_terms(precision):
     """bias + per-sample (time-embedding) bias + residual, as in ResnetBlockDDPM (layers.py:677-689)."""
     from meshdiffusion_b200 import ops
@@ -78,12 +79,12 @@ def test_conv3d_epilogue_terms(precision):
     res = torch.randn(B, C, R, R, R, device="cuda", generator=g)
     ref = F.conv3d(x, w, b, padding=1) + rb[:, :, None, None, None] + res
     y = ops.conv3d(ops.to_ndhwc(x, precision), w, b, rowbias=rb, residual=ops.to_ndhwc(res, precision), precision=precision)
-    err = _rel(ops.from_ndhwc(y), ref)
+    err = _rel(ops.from_ndhwc(y, precision), ref)
     print(f"epilogue {precision}: rel err {err:.3e}")
     assert err < TOL[precision]
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "bf16x3"])
 def test_groupnorm_silu(precision):
     from meshdiffusion_b200 import ops
     B, C, R = 2, 256, 8
@@ -92,13 +93,13 @@ def test_groupnorm_silu(precision):
     gamma = torch.rand(C, device="cuda", generator=g) + 0.5
     beta = torch.randn(C, device="cuda", generator=g) * 0.1
     xin = ops.to_ndhwc(x, precision)
-    xr = ops.from_ndhwc(xin)  # what the kernel actually sees
+    xr = ops.from_ndhwc(xin, precision)  # what the kernel actually sees
     stats = torch.stack([xr.double().sum(dim=(2, 3, 4)), (xr.double() ** 2).sum(dim=(2, 3, 4))], dim=-1).contiguous()
     ref = F.silu(F.group_norm(xr, 32, gamma, beta, eps=1e-6))
-    y = ops.from_ndhwc(ops.groupnorm_act(xin, stats, gamma, beta, silu=True, precision=precision))
+    y = ops.from_ndhwc(ops.groupnorm_act(xin, stats, gamma, beta, silu=True, precision=precision), precision)
     err = _rel(y, ref)
     print(f"gn+silu {precision}: rel err {err:.3e}")
-    assert err < (2e-3 if precision == "tf32" else 1e-2)
+    assert err < {"tf32": 2e-3, "bf16": 1e-2, "bf16x3": 2e-5}[precision]
 
 
 def test_groupnorm_statistics_survive_large_activations():

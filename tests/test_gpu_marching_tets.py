@@ -35,6 +35,31 @@ def test_dmtet_call_matches_reference_golden(case, seed, noisy):
     assert abs(uvs.astype(np.float64).sum() - gold[case + "_uvs_sum"][0]) < 1e-3 * abs(gold[case + "_uvs_sum"][0])
 
 
+@pytest.mark.parametrize("case,seed,noisy", [("sphere", 0, False), ("noisy", 1, True)])
+def test_dmtet_128_matches_reference_golden(case, seed, noisy):
+    """BASELINE configs[3]/[4] grid size: the 128^3 tet grid (253 024 vertices, 1 387 746 tets). Integer outputs bit-exact
+    against the REFERENCE DMTet class through length + sha256 (oracle/make_golden.py::golden_marching_tets_128), float
+    outputs against sampled reference rows and sums."""
+    import hashlib
+    from meshdiffusion_b200.geometry import dmtet
+    gold = load_golden("marching_tets_128.npz")
+    verts, idx = dmtet.load_tet_grid(128)
+    sdf, pos = synth.synthetic_dmtet(verts, seed=seed, noisy=noisy, res=128)
+    out = dmtet.DMTet()(torch.tensor(pos).cuda(), torch.tensor(sdf).cuda(), torch.tensor(idx).long().cuda())
+    names = ["verts", "faces", "uvs", "uv_idx", "face_to_valid_tet", "valid_vert_idx"]
+    for n, t in zip(names, out):
+        a = t.cpu().numpy()
+        assert tuple(a.shape) == tuple(gold[f"{case}_{n}_shape"]), (n, a.shape)
+        if a.dtype.kind in "iu":
+            assert a.dtype == np.int64
+            digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype="<i8").tobytes()).digest(), dtype=np.uint8)
+            assert np.array_equal(digest, gold[f"{case}_{n}_sha256"]), f"{n} is not bit-identical to the reference"
+        else:
+            assert np.allclose(a[gold[f"{case}_{n}_rows"]], gold[f"{case}_{n}_sample"], rtol=1e-5, atol=1e-6), n
+            want = gold[f"{case}_{n}_sum"][0]
+            assert abs(a.astype(np.float64).sum() - want) <= 1e-4 * max(abs(want), 1.0), n
+
+
 def test_batched_extraction_matches_oracle():
     from meshdiffusion_b200.geometry.dmtet import MarchingTets
     verts, idx = _grid()

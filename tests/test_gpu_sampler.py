@@ -87,6 +87,61 @@ def test_partial_sampler_matches_reference_golden():
     assert err < 5e-3
 
 
+def _loop_setup(cfg, B, seed):
+    from meshdiffusion_b200.diffusion import sde_lib
+    model, sd = build_model(cfg, "cuda:0", seed)
+    R = cfg.data.image_size
+    sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda")
+    ts = torch.linspace(sde.T, 1e-3, sde.N, device="cuda")
+    idx = (ts * (sde.N - 1)).long()
+    labels, betas, stds = (ts * (sde.N - 1)).cpu().tolist(), sde.discrete_betas[idx].cpu().tolist(), sde.sqrt_1m_alphas_cumprod[idx].cpu().tolist()
+    mask = sd["mask"].view(R, R, R).cuda().contiguous()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x0 = (torch.randn(B, 4, R, R, R, device="cuda", generator=g) * mask).contiguous()
+    return model, sde, ts, labels, betas, stds, mask, x0
+
+
+@pytest.mark.parametrize("conditional", [False, True])
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "bf16x3"])
+@pytest.mark.parametrize("size", ["tiny", "res64"])
+def test_native_loop_matches_stepwise(size, precision, conditional):
+    """The TIMED path (bench.py `value`): mdb_sampler_run(seed, step0, n) must be bitwise equal to n x [model(x, labels) +
+    mdb_sampler_update(noise=NULL, seed, offset=4*i)] through the public entry points -- same kernels, same Philox
+    counters, and the same replacement conditioning when the partial branch is on."""
+    from helpers import full_config
+    from meshdiffusion_b200 import _native
+    from meshdiffusion_b200.diffusion import sampling
+    import ctypes
+    cfg = tiny_config("res64", precision) if size == "tiny" else full_config("res64", precision)
+    B, n, step0, seed = (3, 5, 2, 77) if size == "tiny" else (2, 3, 400, 78)
+    model, sde, ts, labels, betas, stds, mask, x0 = _loop_setup(cfg, B, 21)
+    net = model.module
+    R = cfg.data.image_size
+    cond = None
+    if conditional:
+        g = torch.Generator(device="cuda").manual_seed(5)
+        partial = torch.sign(torch.randn(1, 1, R, R, R, device="cuda", generator=g))
+        pmask = (torch.rand(1, 1, R, R, R, device="cuda", generator=g) < 0.5).float()
+        cond = sampling._Cond(sde, partial, pmask, 0, ts, B)
+    until = step0 + n - 1  # the last step runs without the replacement, like i >= freeze_iters
+    xa = x0.clone()
+    with torch.no_grad():
+        xma = sampling._native_loop(net, xa, mask.reshape(-1), labels, betas, stds, n, seed, step0, cond, until)
+        xb = x0.clone()
+        L = _native.lib()
+        for i in range(step0, step0 + n):
+            eps = model(xb, torch.full((B,), labels[i], device="cuda"))
+            xmb = torch.empty_like(xb)
+            cs = cond.struct(i) if (cond is not None and i < until) else None
+            _native.check(L.mdb_sampler_update(_native.ptr(eps), _native.ptr(xb), _native.ptr(xmb), None, _native.ptr(mask.reshape(-1)),
+                                               betas[i], stds[i], R ** 3, 4, B, seed, 4 * i,
+                                               ctypes.byref(cs) if cs is not None else None, _native.current_stream()))
+    assert torch.isfinite(xa).all()
+    assert torch.equal(xa, xb) and torch.equal(xma, xmb), "mdb_sampler_run differs from the step-by-step public path"
+    if conditional:
+        assert not torch.equal(xa[:, 0], x0[:, 0])
+
+
 def test_native_loop_runs_and_respects_mask():
     from meshdiffusion_b200.diffusion import sde_lib
     cfg = tiny_config("res64", "bf16")
@@ -134,7 +189,7 @@ def test_in_kernel_philox_noise_moments():
     beta = 0.01
     outs = []
     for step in (0, 1):
-        x, _ = ops.sampler_update(zeros, zeros.clone(), None, mask, beta, 1.0, seed=1234, offset=step)
+        x, _ = ops.sampler_update(zeros, zeros.clone(), None, mask, beta, 1.0, seed=1234, offset=4 * step)
         z = x / beta ** 0.5
         live = z[:, :, :, :, R // 2:]
         assert torch.all(z[:, :, :, :, : R // 2] == 0)
