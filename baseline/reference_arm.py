@@ -67,8 +67,10 @@ def load(device):
 def build(device, seed=0):
     ref, config = load(device)
     torch.manual_seed(seed)
-    model = ref["mutils"].create_model(config)  # nn.DataParallel(DDPMRes64(config)).to(device), models/utils.py:88-96
-    net = model.module
+    # models/utils.py:88-96 with the reference's own `use_parallel=False` switch: nn.DataParallel would claim every visible GPU
+    # (and refuses a CPU-resident module on a GPU box); one device is what both arms measure
+    model = ref["mutils"].create_model(config, use_parallel=False).to(config.device)
+    net = model
     init = ref["layers"].default_init(1.0)
     with torch.no_grad():
         for name, p in net.named_parameters():

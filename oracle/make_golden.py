@@ -311,6 +311,52 @@ def golden_marching_tets():
     print("grid_mask_64 == scatter of tet vertices:", int(mask.sum()), "voxels")
 
 
+def golden_dataset_items():
+    """tests/golden/dataset_items.npz: items of the REFERENCE ShapeNetDMTetDataset (lib/dataset/shapenet_dmtet_dataset.py:8-54)
+    on four synthetic 7^3 shapes under an 8^3 grid mask with a 3-id filter list -- `aug=False` then `aug=True` (global RNG
+    seeded with 100 + index before each item, which fixes the jitter draw). The inputs (`raw`, `mask`, `filter`) are part of
+    the fixture: when the file exists they are re-used and the regenerated items must equal the committed ones bit for bit;
+    otherwise they are drawn from seed 7."""
+    import importlib.util
+    import tempfile
+    spec = importlib.util.spec_from_file_location("ref_dataset", os.path.join(REF, "lib/dataset/shapenet_dmtet_dataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = os.path.join(GOLD, "dataset_items.npz")
+    old = np.load(path) if os.path.exists(path) else None
+    if old is not None:
+        raw, mask, filt = old["raw"], old["mask"], old["filter"]
+    else:
+        g = torch.Generator().manual_seed(7)
+        raw = (torch.randn(4, 4, 7, 7, 7, generator=g) * (torch.rand(4, 4, 7, 7, 7, generator=g) < 0.6)).numpy().astype(np.float32)
+        mask = (torch.rand(1, 1, 8, 8, 8, generator=g) < 0.7).float().numpy()
+        filt = np.array([0, 2, 3], np.int64)
+    items = []
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for i, r in enumerate(raw):
+            p = os.path.join(tmp, f"shape_{i}.pt")
+            torch.save(torch.tensor(r), p)
+            paths.append(p)
+        meta, fpath = os.path.join(tmp, "meta.json"), os.path.join(tmp, "filter.json")
+        json.dump(paths, open(meta, "w"))
+        json.dump([int(v) for v in filt], open(fpath, "w"))
+        for aug in (False, True):
+            ds = mod.ShapeNetDMTetDataset(meta, torch.tensor(mask), deform_scale=3.0, aug=aug, filter_meta_path=fpath,
+                                          normalize_sdf=True, extension="pt")
+            assert len(ds) == len(filt)
+            for i in range(len(ds)):
+                torch.manual_seed(100 + i)
+                items.append(ds[i].numpy())
+    items = np.stack(items)
+    if old is not None:
+        assert np.array_equal(items, old["items"]), "reference dataset items differ from the committed golden"
+        print(f"dataset items: {items.shape[0]} items of the reference class == committed golden (bit-identical)")
+        return
+    np.savez_compressed(path, raw=raw, mask=mask, items=items, filter=filt)
+    print("dataset items written:", items.shape)
+
+
 def int_digest(a):
     """sha256 of an integer array as little-endian int64 -- pins every entry without storing 10^5 of them."""
     import hashlib
@@ -358,6 +404,7 @@ def golden_marching_tets_128(mt):
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     ref = import_reference()
+    golden_dataset_items()
     golden_marching_tets()
     golden_mesh_ops()
     golden_unet_forward(ref)
