@@ -250,7 +250,7 @@ int mdb_sampler_run(mdb_unet* n, float* x, float* x_mean, const float* mask, con
   if (cond && cond->noise) throw std::runtime_error("mdb: mdb_sampler_run draws its noise in-kernel (cond->noise must be NULL)");
   for (int i = 0; i < n_steps; ++i) {
     fill_kernel<<<(B + 127) / 128, 128, 0, s>>>(labels_buf, labels[i], B);
-    n->net->forward(x, labels_buf, eps_buf, B, s);
+    n->net->forward(x, labels_buf, eps_buf, B, s, /*allow_graph=*/true);
     SamplerUpdateArgs a{};
     a.eps = eps_buf; a.x = x; a.x_mean = x_mean; a.noise = nullptr; a.mask = mask; a.beta = betas[i]; a.stdv = stds[i];
     // curand_normal consumes two 32-bit Philox outputs and `offset` counts single outputs: 4*i gives every step its own

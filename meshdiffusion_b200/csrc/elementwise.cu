@@ -608,6 +608,30 @@ void launch_add_vec(const float* a, const float* b, float* out, int n, cudaStrea
   MDB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------ sub-pixel upsample-conv weights
+__global__ void upconv_weights_kernel(const float* __restrict__ w, float* __restrict__ w8, long long pairs) {
+  const long long total = pairs * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 7), par = (int)((i >> 3) & 7);
+    const long long oc = i >> 6;  // (co, ci) pair
+    const int ez = e >> 2, ey = (e >> 1) & 1, ex = e & 1;
+    const int pz = par >> 2, py = (par >> 1) & 1, px = par & 1;
+    // original taps folded into effective tap (parity q, e): q=0: e0 <- {0}, e1 <- {1,2}; q=1: e0 <- {0,1}, e1 <- {2}
+    auto lo = [](int q, int t) { return q == 0 ? (t == 0 ? 0 : 1) : (t == 0 ? 0 : 2); };
+    auto hi = [](int q, int t) { return q == 0 ? (t == 0 ? 0 : 2) : (t == 0 ? 1 : 2); };
+    float acc = 0.f;
+    for (int dz = lo(pz, ez); dz <= hi(pz, ez); ++dz)
+      for (int dy = lo(py, ey); dy <= hi(py, ey); ++dy)
+        for (int dx = lo(px, ex); dx <= hi(px, ex); ++dx) acc += w[oc * 27 + (dz * 3 + dy) * 3 + dx];
+    w8[((long long)par * pairs + oc) * 8 + e] = acc;
+  }
+}
+void launch_upconv_weights(const float* w, float* w8, int Cout, int Cin, cudaStream_t s) {
+  const long long pairs = (long long)Cout * Cin;
+  upconv_weights_kernel<<<grid_for(pairs * 64, 256), 256, 0, s>>>(w, w8, pairs);
+  MDB_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------ ancestral sampling update
 // Same operation order as the reference's eager fp32 ops (no FMA contraction) so that, given identical eps and
 // noise, x and x_mean are bit-identical: score = -eps/std; x_mean = (x + beta*score)/sqrt(1-beta);

@@ -69,6 +69,10 @@ void launch_split_reduce(const SplitReduceArgs& a, int B, cudaStream_t s);
 
 void launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
 
+// Sub-pixel form of Upsample(nearest x2) + conv3^3 (layers.py:611-623): w OIDHW [Cout][Cin][3][3][3] -> w8
+// [8 parities (pz,py,px)][Cout][Cin][2][2][2] with, per axis, parity 0: {W0, W1+W2}, parity 1: {W0+W1, W2}.
+void launch_upconv_weights(const float* w, float* w8, int Cout, int Cin, cudaStream_t s);
+
 // Ancestral-sampling predictor update fused with the score scaling and both mask multiplies
 // (sampling.py:222-230,476-478; models/utils.py:191-198). All fp32, NCDHW [B][4][V]; mask [V].
 struct SamplerUpdateArgs {

@@ -110,7 +110,7 @@ GemmOp::~GemmOp() {
 }
 
 void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N, void* out, long long osx,
-                                long long osy, long long osz, long long osb, bool out_fp32) {
+                                long long osy, long long osz, long long osb, bool out_fp32, long long lo_off) {
   prec = pr;
   geo = pick_geometry(X, Y, Z);
   if (geo.bx * geo.by * geo.bz * geo.bb != kBlockM) throw std::runtime_error("mdb: unsupported tile geometry");
@@ -136,7 +136,7 @@ void GemmOp::set_output_strided(Precision pr, int X, int Y, int Z, int B, int N,
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.out_lo_off = 0;
   if (prec == kBF16X3 && !out_fp32) {  // (hi, lo) rows: physical pitch 2x the logical one, lo parts one logical row behind
-    p.out_lo_off = osx;
+    p.out_lo_off = lo_off >= 0 ? lo_off : osx;
     p.osx *= 2; p.osy *= 2; p.osz *= 2; p.osb *= 2;
   }
   {
@@ -263,6 +263,28 @@ void GemmOp::add_conv_w(const std::vector<Act>& srcs, const WSrc& wsrc, int k, i
     }
   } else {
     throw std::runtime_error("mdb: unsupported stride");
+  }
+}
+
+void GemmOp::add_conv_up2(const Act& s, const float* w8, int px, int py, int pz) {
+  const int KB = kb_elems(prec);
+  const int ws = add_wsrc(WSrc{w8, 8LL * s.C, 8, 1, s.C});
+  flops += 2.0 * p.X * p.Y * p.Z * p.Bn * (double)p.N * s.C * 8;
+  const bool x3 = prec == kBF16X3;
+  // effective tap e in {0,1} of an axis with output parity q reads the input at offset e - 1 + q
+  const bool reuse = geo.bz == 1 && geo.bb == 1 && geo.bx * (geo.by + 1) <= kAStageRows && p.Y >= geo.by;
+  const int tm = add_amap(s, reuse ? 1 : 0);
+  const int tl = x3 ? add_amap(s, reuse ? 1 : 0, 1, 0, 0, 0, 1) : tm;
+  for (int c0 = 0; c0 < s.C; c0 += KB) {
+    for (int ez = 0; ez < 2; ++ez)
+      for (int ex = 0; ex < 2; ++ex) {
+        if (reuse) {  // the two y-taps share one box with a 1-row halo
+          add_load_x(tm, tl, 2, geo.bx * (geo.by + 1), geo.bx, ex - 1 + px, -1 + py, ez - 1 + pz, c0, ws, c0, (ez * 2) * 2 + ex, 2);
+        } else {
+          for (int ey = 0; ey < 2; ++ey)
+            add_load_x(tm, tl, 1, kBlockM, 0, ex - 1 + px, ey - 1 + py, ez - 1 + pz, c0, ws, c0, (ez * 2 + ey) * 2 + ex, 0);
+        }
+      }
   }
 }
 

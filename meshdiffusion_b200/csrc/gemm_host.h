@@ -85,8 +85,9 @@ class GemmOp {
 
   // output geometry; must be called first
   void set_output(Precision prec, int X, int Y, int Z, int B, int N, void* out, long long ldc, bool out_fp32);
+  // lo_off (X3 only): logical distance from the hi to the lo parts of an output row; default = osx (dense rows)
   void set_output_strided(Precision prec, int X, int Y, int Z, int B, int N, void* out, long long osx, long long osy,
-                          long long osz, long long osb, bool out_fp32);
+                          long long osz, long long osb, bool out_fp32, long long lo_off = -1);
   // adds a 5-D A tensor map over `a` (optionally a stride-2 parity sub-grid) with a (KB, bx, by+halo, bz, bb) box.
   // part: 0 = the tensor itself / the hi parts of an X3 tensor, 1 = its lo parts
   int add_amap(const Act& a, int halo_rows_y, int sub_stride = 1, int px = 0, int py = 0, int pz = 0, int part = 0);
@@ -102,6 +103,12 @@ class GemmOp {
   // concatenation of `srcs`; weight OIDHW fp32 [N][sum C][k^3].
   void add_conv(const std::vector<Act>& srcs, const float* w_oidhw, int ksize, int stride);
   void add_conv_w(const std::vector<Act>& srcs, const WSrc& w, int ksize, int stride);
+  // One output-parity class of Upsample (nearest x2, layers.py:611-623) followed by its 3^3 convolution, evaluated on the
+  // LOW-resolution input: output voxel 2h+p sees only two distinct input voxels per axis (h-1, h for p = 0; h, h+1 for
+  // p = 1), so the 27 taps collapse to a 2^3 kernel whose weights are sums of the original ones (w8: [N][C][2][2][2] fp32,
+  // built by launch_upconv_weights). The op's output geometry must be the low-resolution grid with strides into the
+  // high-resolution tensor (set_output_strided). 8/27 of the FLOPs, and the 8x larger tensor is never materialised.
+  void add_conv_up2(const Act& src, const float* w8, int px, int py, int pz);
   // conv data gradient: N = cin_total of the forward conv, A = dY (C = forward Cout), weight fp32 OIDHW of the forward
   void add_conv_dgrad(const Act& dy, const float* w_oidhw, int cin_total, int ksize);
   // 1x1x1 projection of the channel concatenation of `srcs` with W[in][out] (NIN layout) or [out][in] (Linear/conv).

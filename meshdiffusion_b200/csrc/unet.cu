@@ -346,6 +346,30 @@ TensP UNet::upsample(const TensP& x, int midx) {
   const int C = x->C, R = x->R * 2;
   float* w = P(pre + "Conv_0.weight", {C, C, 3, 3, 3});
   float* b = P(pre + "Conv_0.bias", {C});
+  if (!train_) {
+    // Inference: sub-pixel form. Each of the 8 output-parity classes is a 2^3 convolution over the LOW-resolution tensor
+    // (8/27 of the FLOPs) writing its strided share of the output; the upsampled tensor never exists. The training plan
+    // keeps the materialised form below (its backward differentiates exactly that graph).
+    TensP out = new_act(C, R, true);
+    if (!dry_) {
+      const int r = x->R, mb = cfg_.max_batch;
+      float* w8 = (float*)dmalloc((size_t)64 * C * C * sizeof(float));
+      commit_steps_.push_back({"upw:" + pre, [=](cudaStream_t s, int) { launch_upconv_weights(w, w8, C, C, s); }});
+      const long long es = esize(prec_) * parts(prec_);
+      for (int par = 0; par < 8; ++par) {
+        const int px = par & 1, py = (par >> 1) & 1, pz = par >> 2;
+        GemmOp* g = new_gemm("up" + std::to_string(midx) + ".conv.p" + std::to_string(par));
+        char* base = (char*)out->ptr + (((long long)pz * R + py) * R + px) * C * es;
+        g->set_output_strided(prec_, r, r, r, mb, C, base, 2LL * C, 2LL * R * C, 2LL * R * R * C, (long long)R * R * R * C, false, C);
+        g->add_conv_up2(act_of(x), w8 + (size_t)par * C * C * 8, px, py, pz);
+        g->set_bias(b);
+        g->set_stats(out->stats);
+        g->finalize(0, false);
+        add_step(g->name, [g](cudaStream_t s, int B) { g->launch(s, B); });
+      }
+    }
+    return out;
+  }
   TensP up = new_act(C, R, false);
   if (!dry_) {
     const void* src = x->ptr; void* dst = up->ptr; const int r = x->R; const int tf = prec_ == kTF32;
@@ -563,6 +587,7 @@ UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(precision_fr
   if (cfg_.image_size % (1 << (cfg_.n_levels - 1)) != 0) throw std::runtime_error("mdb: image_size not divisible by 2^(levels-1)");
   if (cfg_.nf % 32 != 0) throw std::runtime_error("mdb: nf must be a multiple of 32 (GroupNorm(32))");
   train_ = cfg_.training != 0;
+  if (const char* e = getenv("MDB_GRAPH_MAX_BATCH")) graph_max_batch_ = atoi(e);  // 0 disables graph replay
   if (train_ && prec_ != kBF16) throw std::runtime_error("mdb: the training plan is built for bf16 operands");
   dry_ = true;
   build();
@@ -592,6 +617,8 @@ UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(precision_fr
 }
 
 UNet::~UNet() {
+  drop_graphs();
+  if (capture_stream_) cudaStreamDestroy(capture_stream_);
   gemms_.clear();
   bwd_gemms_.clear();
   wgrads_.clear();
@@ -618,6 +645,7 @@ void UNet::get_param(const std::string& name, float* dst, long long numel, bool 
 }
 
 void UNet::commit(cudaStream_t s) {
+  drop_graphs();  // packed weights are rewritten in place, but derived pointers are only guaranteed per commit
   for (auto& st : commit_steps_) st.fn(s, 1);
   for (auto& g : gemms_) g->repack(s);
   for (auto& g : bwd_gemms_) g->repack(s);
@@ -625,10 +653,45 @@ void UNet::commit(cudaStream_t s) {
   committed_ = true;
 }
 
-void UNet::forward(const float* x, const float* labels, float* out, int B, cudaStream_t s) {
+void UNet::drop_graphs() {
+  for (auto& g : graphs_) if (g.exec) cudaGraphExecDestroy(g.exec);
+  graphs_.clear();
+}
+
+void UNet::forward(const float* x, const float* labels, float* out, int B, cudaStream_t s, bool allow_graph) {
   if (!committed_) throw std::runtime_error("mdb: parameters changed, call commit() before forward()");
   if (B < 1 || B > cfg_.max_batch) throw std::runtime_error("mdb: batch out of range");
   rt_x_ = x; rt_labels_ = labels; rt_out_ = out;
+  if (allow_graph && !train_ && B <= graph_max_batch_) {
+    FwdGraph* fg = nullptr;
+    for (auto& g : graphs_) if (g.x == x && g.labels == labels && g.out == out && g.B == B) fg = &g;
+    if (!fg) {
+      if (graphs_.size() >= 8) drop_graphs();
+      graphs_.push_back({x, labels, out, B, 0, nullptr});
+      fg = &graphs_.back();
+    }
+    if (fg->exec) { MDB_CUDA_CHECK(cudaGraphLaunch(fg->exec, s)); return; }
+    if (fg->uses++ >= 1) {
+      // second call with these buffers: capture (the first ran eagerly, so every kernel attribute is configured)
+      if (!capture_stream_) MDB_CUDA_CHECK(cudaStreamCreateWithFlags(&capture_stream_, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      MDB_CUDA_CHECK(cudaStreamBeginCapture(capture_stream_, cudaStreamCaptureModeThreadLocal));
+      try {
+        MDB_CUDA_CHECK(cudaMemsetAsync(stats_base_, 0, stats_doubles_ * sizeof(long long), capture_stream_));
+        for (auto& st : steps_) st.fn(capture_stream_, B);
+      } catch (...) {
+        cudaStreamEndCapture(capture_stream_, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      MDB_CUDA_CHECK(cudaStreamEndCapture(capture_stream_, &graph));
+      cudaError_t e = cudaGraphInstantiate(&fg->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { fg->exec = nullptr; MDB_CUDA_CHECK(e); }
+      MDB_CUDA_CHECK(cudaGraphLaunch(fg->exec, s));
+      return;
+    }
+  }
   MDB_CUDA_CHECK(cudaMemsetAsync(stats_base_, 0, stats_doubles_ * sizeof(long long), s));
   for (auto& st : steps_) st.fn(s, B);
 }

@@ -87,7 +87,10 @@ class UNet {
   // after (re)loading parameters: derived vectors, constant stem field, weight packing
   void commit(cudaStream_t s);
   // x: fp32 NCDHW [B][Cin][R^3]; labels: fp32 [B]; out: fp32 NCDHW [B][Cin][R^3]
-  void forward(const float* x, const float* labels, float* out, int B, cudaStream_t s);
+  // allow_graph: the caller promises that (x, labels, out) are the SAME buffers call after call (the sampler loop): for
+  // small batches, where the ~200 launches of a step are launch-latency bound, the whole step is then captured once
+  // into a CUDA graph (on a private capture stream) and replayed on `s`
+  void forward(const float* x, const float* labels, float* out, int B, cudaStream_t s, bool allow_graph = false);
   // training engines only. Dropout of the next forward()/backward() pair (p = 0 disables; same seed in both).
   void set_dropout(float p, unsigned long long seed);
   // dout: fp32 NCDHW dL/d(out) of the preceding forward() (same x, labels, B). grads: flat fp32 buffer holding the
@@ -133,6 +136,12 @@ class UNet {
   std::vector<Step> steps_, commit_steps_;
   bool committed_ = false;
   double flops_ = 0;
+  // CUDA-graph replay of the forward plan (allow_graph): one instantiated graph per (x, labels, out, B)
+  struct FwdGraph { const float* x; const float* labels; float* out; int B; int uses; cudaGraphExec_t exec; };
+  std::vector<FwdGraph> graphs_;
+  cudaStream_t capture_stream_ = nullptr;
+  int graph_max_batch_ = 8;
+  void drop_graphs();
   // runtime pointers
   const float* rt_x_ = nullptr;
   const float* rt_labels_ = nullptr;
