@@ -181,7 +181,15 @@ int GemmOp::add_amap(const Act& a, int halo, int sub, int px, int py, int pz, in
 void GemmOp::add_load_x(int tm_hi, int tm_lo, int nk, int rows, int jrows, int dx, int dy, int dz, int c0, int wsrc,
                         int wc0, int tap0, int tapj) {
   if (prec != kBF16X3) { add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0); return; }
-  // small terms first: (A lo, W hi) and (A hi, W lo) are ~2^-9 of the leading product
+  if (pair) {
+    // CTA pairs: a (hi, lo) couple of stages -- (A hi, W hi) then (A lo, W lo) -- from which the MMA warp forms the three
+    // products itself (GemmSeg::x3pair): every operand byte crosses L2 -> SMEM once
+    add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0);
+    add_load(tm_lo, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 1);
+    return;
+  }
+  // K-extension form (single CTAs: small problems, split-K). Small terms first: (A lo, W hi) and (A hi, W lo) are ~2^-9
+  // of the leading product
   add_load(tm_lo, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0);
   add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 1);
   add_load(tm_hi, nk, rows, jrows, dx, dy, dz, c0, wsrc, wc0, tap0, tapj, 0);
@@ -446,12 +454,15 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   p.loads = d_loads;
   p.n_loads = (int)loads.size();
   if (p.splits < 1) p.splits = 1;
-  // pipeline segments: runs of identical entries; plain (nk == 1) entries are paired two per stage
+  // pipeline segments: runs of identical entries; plain (nk == 1) entries are paired two per stage. The stage size is the
+  // largest group of this op and the ring takes as many stages as fit in the 227 KB next to the epilogue scratch.
   {
     const int btile = block_n * kRowBytes / (pair ? 2 : 1);
-    const int stage_bytes = pair ? (2 * 128 * kRowBytes + 2 * 64 * kRowBytes) : (kAStageBytes + 3 * 128 * kRowBytes);
+    const int max_stage = pair ? (2 * 128 * kRowBytes + 2 * 64 * kRowBytes) : (kAStageBytes + 3 * 128 * kRowBytes);
+    const bool x3pair = pair && prec == kBF16X3;
+    stage_need = 0;
     p.n_segs = 0;
-    auto push = [&](int n_groups, int epg, const LoadEntry& e) {
+    auto push = [&](int n_groups, int epg, const LoadEntry& e, int couple) {
       if (n_groups <= 0) return;
       if (p.n_segs >= kMaxSegs) throw std::runtime_error("mdb: too many pipeline segments");
       GemmSeg sg{};
@@ -459,7 +470,10 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
       sg.a_bytes = e.rows * kRowBytes;
       sg.a_stride = (sg.a_bytes + 1023) / 1024 * 1024;
       sg.jbytes = e.jrows * kRowBytes;
-      if (epg * (sg.a_stride + e.nk * btile) > stage_bytes) throw std::runtime_error("mdb: pipeline group exceeds the stage size");
+      sg.x3pair = couple;
+      const int need = epg * (sg.a_stride + e.nk * btile);
+      if (need > max_stage) throw std::runtime_error("mdb: pipeline group exceeds the stage size");
+      if (need > stage_need) stage_need = need;
       p.segs[p.n_segs++] = sg;
       p.total_groups += n_groups;
     };
@@ -469,11 +483,14 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
       size_t j = i;
       while (j < loads.size() && loads[j].nk == loads[i].nk && loads[j].rows == loads[i].rows && loads[j].jrows == loads[i].jrows) ++j;
       const int run = (int)(j - i);
-      if (loads[i].nk == 1 && 2 * (loads[i].rows * kRowBytes + btile) <= stage_bytes) {
-        push(run / 2, 2, loads[i]);
-        push(run % 2, 1, loads[i]);
+      if (x3pair) {
+        if (run % 2 != 0) throw std::runtime_error("mdb: X3 stage couples need an even run of entries");
+        push(run, 1, loads[i], 1);
+      } else if (loads[i].nk == 1 && 2 * (loads[i].rows * kRowBytes + btile) <= max_stage) {
+        push(run / 2, 2, loads[i], 0);
+        push(run % 2, 1, loads[i], 0);
       } else {
-        push(run, 1, loads[i]);
+        push(run, 1, loads[i], 0);
       }
       i = j;
     }
@@ -495,11 +512,11 @@ template <int BN, bool TF32, bool CG2, bool GNB = false, bool X3 = false>
 static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured[64] = {};  // the attribute is per device
   auto kern = gemm_tc_kernel<BN, TF32, CG2, GNB, X3>;
-  constexpr int smem = GemmCfg<BN, CG2>::kSmemBytes;
+  const int smem = GemmCfg<BN, CG2>::kFixedBytes + p.n_stages * p.stage_bytes;
   int dev = 0;
   MDB_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev >= 64 || !configured[dev]) {
-    MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MDB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     if (dev < 64) configured[dev] = true;
   }
   if (CG2) {
@@ -521,6 +538,19 @@ static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
 
 void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
   GemmParams p = this->p;
+  {
+    // operand ring of this op: stage = its largest pipeline group, as many stages as the 227 KB allow
+    const int fixed = 1024 + 24 * block_n * 4 + (2 * kMaxStages + 4) * 8 + 16;  // GemmCfg<block_n, *>::kFixedBytes
+    p.stage_bytes = (stage_need + 1023) / 1024 * 1024;
+    int ns = (kMaxDynSmem - fixed) / p.stage_bytes;
+    // measured (profiles/r02_bench_stages_4_vs_5.txt): a fifth 42 KB stage fits for the halo convolutions but is 1-2 %
+    // SLOWER in all three operand modes than four -- the feed is bounded by L2 -> SMEM bytes per MMA, not by bytes in flight
+    int cap = 4;
+    if (const char* e = getenv("MDB_MAX_STAGES")) { const int c = atoi(e); if (c >= 2) cap = c; }
+    if (ns > cap) ns = cap;
+    p.n_stages = ns > kMaxStages ? kMaxStages : ns;
+    if (p.n_stages < 2) throw std::runtime_error("mdb: operand ring needs at least two stages");
+  }
   if (B > 0) {
     if (B > this->p.Bn) throw std::runtime_error("mdb: batch exceeds the batch the op was built for");
     p.Bn = B;

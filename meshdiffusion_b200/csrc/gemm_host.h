@@ -149,6 +149,7 @@ class GemmOp {
  private:
   Geometry geo{};
   bool b_from_act = false;
+  int stage_need = 0;  // bytes of the largest pipeline group (decides the stage size / count at launch)
   long long b_lo_off = 0;  // X3 activation-B: K coordinate of the lo parts
   void encode_bmap(void* ptr, int K, int N, int batch, long long row_stride_bytes, long long batch_stride_bytes);
 };

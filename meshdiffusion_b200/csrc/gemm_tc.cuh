@@ -57,6 +57,11 @@ struct GemmSeg {
   int a_bytes;   // bytes of one A box (rows * 128) -- the TMA transaction size
   int a_stride;  // distance between the group's A boxes in the stage (multiple of 1024)
   int jbytes;    // A-descriptor advance between the k-steps of one entry (halo reuse)
+  // X3 on CTA pairs: the groups of this run come in (hi, lo) couples occupying two consecutive stages -- stage k holds the
+  // hi parts (A hi box, W hi tiles), stage k+1 the lo parts -- and the MMA warp issues hi*hi, hi*lo and lo*hi from the two
+  // resident stages: every operand byte is fetched from L2 once for its three products (the plain K-extension form
+  // fetches A hi and W hi twice).
+  int x3pair;
 };
 constexpr int kMaxSegs = 8;
 
@@ -81,6 +86,7 @@ struct GemmParams {
   int batch_fastest;   // enumerate the batch axis first among M-tiles (residual shared by all samples stays in L2)
   int kb_elems;        // K elements per k-step (64 bf16 / 32 tf32)
   int b_explicit_k;    // B tile K coordinates come from LoadEntry::wc0 instead of the running k column
+  int n_stages, stage_bytes;  // shared-memory operand ring: as many stages as fit next to the epilogue scratch
   // X3 (split bf16) epilogue: the lo parts of the output / residual rows sit this many elements behind the hi parts
   long long out_lo_off, res_lo_off;
   // epilogue
@@ -111,19 +117,26 @@ struct GemmParams {
   float* gnb_part;      // [tiles_m * bb][N][2]
 };
 
+constexpr int kMaxStages = 6;
+constexpr int kMaxDynSmem = 232448;  // 227 KB: the opt-in limit of dynamic shared memory per block on sm_100
 template <int BLOCK_N, bool CG2>
 struct GemmCfg {
-  static constexpr int kStages = CG2 ? 4 : 3;
   // weight tile bytes staged per CTA per k-step (a CTA pair splits the N rows of the tile between its two CTAs)
   static constexpr int kBTileBytes = BLOCK_N * kRowBytes / (CG2 ? 2 : 1);
-  // a stage holds one halo box + 3 weight tiles, or 2 plain boxes + 2 tiles
-  static constexpr int kStageBytes = CG2 ? (2 * 128 * kRowBytes + 2 * 64 * kRowBytes) : (kAStageBytes + 3 * 128 * kRowBytes);
   // The whole TMEM (512 columns) is taken: with one CTA per SM the allocation then always starts at column 0, so
   // accumulator addresses are compile-time/uniform values and the MMA issue loop needs no per-instruction R2UR.
   static constexpr int kTmemCols = 512;
   static constexpr int kStatsFloats = 24 * BLOCK_N;  // 2 x [4 warps][sum,sumsq][N] column partials + 2 x [4 segs][N] bias
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatsFloats * 4 +
-                                    (2 * kStages + 4) * 8 + 16;
+  // everything but the operand ring: alignment slack, epilogue scratch, mbarriers (sized for kMaxStages), TMEM slot
+  static constexpr int kFixedBytes = 1024 + kStatsFloats * 4 + (2 * kMaxStages + 4) * 8 + 16;
+  // stage size / count of an op whose largest pipeline group needs `need` bytes: the ring takes whatever is left of
+  // the 227 KB (more stages = more TMA bytes in flight per SM, which is what bounds the L2 -> SMEM feed rate)
+  static int stage_bytes(int need) { return (need + 1023) / 1024 * 1024; }
+  static int stages(int need) {
+    const int n = (kMaxDynSmem - kFixedBytes) / stage_bytes(need);
+    return n > kMaxStages ? kMaxStages : n;
+  }
+  static int smem_bytes(int need) { return kFixedBytes + stages(need) * stage_bytes(need); }
 };
 
 // dropout hash shared with the GroupNorm kernels (backward.cuh::drop_hash64)
@@ -229,16 +242,17 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 template <int BLOCK_N, bool TF32, bool CG2, bool GNB = false, bool X3 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, CG2>;
-  constexpr int NS = Cfg::kStages;
+  const int NS = p.n_stages;
+  const uint32_t kStageBytesRt = (uint32_t)p.stage_bytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_stats = reinterpret_cast<float*>(smem + NS * Cfg::kStageBytes);
+  float* s_stats = reinterpret_cast<float*>(smem + NS * p.stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + Cfg::kStatsFloats);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
   const uint32_t stage0 = smem_u32(smem);
-  const uint32_t full = smem_u32(bars), empty = full + 8 * NS;
-  const uint32_t t_full = empty + 8 * NS, t_empty = t_full + 16;
+  const uint32_t full = smem_u32(bars), empty = full + 8 * kMaxStages;
+  const uint32_t t_full = empty + 8 * kMaxStages, t_empty = t_full + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -326,7 +340,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           if (seg.epg > 1) raw1 = __ldg(reinterpret_cast<const uint4*>(p.loads + l + 1));
           mbar_wait(empty + 8 * st, ph ^ 1);
           if (elect_one()) {
-            const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
+            const uint32_t sbase = stage0 + st * kStageBytesRt;
             int kc = kcol;
             if constexpr (CG2) {
               // both CTAs credit the LEADER's full barrier; only the leader arms it (with the pair's total bytes)
@@ -361,7 +375,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           __syncwarp();
           kcol += seg.epg * seg.nk * p.kb_elems;
           l += seg.epg;
-          if (++st == NS) { st = 0; ph ^= 1; }
+          if (++st == (uint32_t)NS) { st = 0; ph ^= 1; }
         }
       }
     }
@@ -382,12 +396,52 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       for (int sg = 0; sg < p.n_segs; ++sg) {
         const GemmSeg seg = p.segs[sg];
         const uint32_t b_base = seg.epg * seg.a_stride;
+        if constexpr (X3 && CG2) {
+          if (seg.x3pair) {
+            // (hi, lo) stage couples: hi*hi as soon as the hi stage has landed, then hi*lo and lo*hi
+            for (int g = 0; g < seg.n_groups; g += 2, gi += 2) {
+              const uint32_t s0 = st, ph0 = ph;
+              if (++st == (uint32_t)NS) { st = 0; ph ^= 1; }
+              const uint32_t s1 = st, ph1 = ph;
+              if (++st == (uint32_t)NS) { st = 0; ph ^= 1; }
+              const uint32_t base0 = stage0 + s0 * kStageBytesRt, base1 = stage0 + s1 * kStageBytesRt;
+              mbar_wait(full + 8 * s0, ph0);
+              tc_fence_after();
+              if (elect_one()) {
+                for (int j = 0; j < seg.nk; ++j) {
+                  const uint32_t a_lo = desc_lo(base0 + j * seg.jbytes);
+                  const uint32_t b_lo = desc_lo(base0 + seg.a_stride + j * Cfg::kBTileBytes);
+#pragma unroll
+                  for (int k = 0; k < kRowBytes / 32; ++k) { umma_lo_cg2<TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accumulate); accumulate = 1; }
+                }
+              }
+              __syncwarp();
+              mbar_wait(full + 8 * s1, ph1);
+              tc_fence_after();
+              if (elect_one()) {
+                for (int j = 0; j < seg.nk; ++j) {
+                  const uint32_t a0 = desc_lo(base0 + j * seg.jbytes), a1 = desc_lo(base1 + j * seg.jbytes);
+                  const uint32_t b0 = desc_lo(base0 + seg.a_stride + j * Cfg::kBTileBytes);
+                  const uint32_t b1 = desc_lo(base1 + seg.a_stride + j * Cfg::kBTileBytes);
+#pragma unroll
+                  for (int k = 0; k < kRowBytes / 32; ++k) umma_lo_cg2<TF32>(d_tmem, a0 + 2 * k, b1 + 2 * k, idesc, 1u);
+#pragma unroll
+                  for (int k = 0; k < kRowBytes / 32; ++k) umma_lo_cg2<TF32>(d_tmem, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+                }
+                umma_commit_pair(empty + 8 * s0);
+                umma_commit_pair(empty + 8 * s1);
+              }
+              __syncwarp();
+            }
+            continue;
+          }
+        }
         for (int g = 0; g < seg.n_groups; ++g, ++gi) {
           if (gi < g_lo || gi >= g_hi) continue;
           mbar_wait(full + 8 * st, ph);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sbase = stage0 + st * Cfg::kStageBytes;
+            const uint32_t sbase = stage0 + st * kStageBytesRt;
             for (int e = 0; e < seg.epg; ++e) {
               for (int j = 0; j < seg.nk; ++j) {
                 const uint32_t a_lo = desc_lo(sbase + e * seg.a_stride + j * seg.jbytes);
@@ -403,7 +457,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             if constexpr (CG2) umma_commit_pair(empty + 8 * st); else umma_commit(empty + 8 * st);
           }
           __syncwarp();
-          if (++st == NS) { st = 0; ph ^= 1; }
+          if (++st == (uint32_t)NS) { st = 0; ph ^= 1; }
         }
       }
       if (elect_one()) { if constexpr (CG2) umma_commit_pair(t_full + 8 * acc); else umma_commit(t_full + 8 * acc); }
