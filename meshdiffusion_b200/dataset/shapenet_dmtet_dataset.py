@@ -82,3 +82,26 @@ class ShapeNetDMTetDataset(Dataset):
         if missing > 0:
             grid = F.pad(grid, (0, missing, 0, missing, 0, missing, 0, 0))
         return grid
+
+
+def augment_on_device(raw, grid_mask, shifts, normalize_sdf=True, fix_sign_axis=False):
+    """The per-item pipeline above for a whole batch on the GPU: raw [B,4,r,r,r] grids as loaded (device
+    tensor), grid_mask [1,1,R,R,R], shifts [B,3] ~ U(0,1) (the `torch.rand(3)` draw of each item). Returns [B,4,R,R,R].
+    Same arithmetic, same order as `ShapeNetDMTetDataset.__getitem__` with aug=True, so given the items' draws the result
+    is bit-identical to stacking the loader's items (tests/test_host.py::test_on_device_augmentation_matches_items)."""
+    grid = raw.clone()
+    R, r = grid_mask.size(-1), grid.size(-1)
+    if normalize_sdf:
+        region = grid[:, :1] if fix_sign_axis else grid[:, :, :1]   # the reference's quirk: first X-slab of every channel
+        s = torch.sign(region)
+        s[s == 0] = 1.0
+        region.copy_(s)
+    occupied = grid[:, 1:].abs().sum(dim=1, keepdim=True) != 0
+    shift = (shifts.to(grid.device)[:, :, None, None, None] - 0.5) * _JITTER
+    grid[:, 1:] = grid[:, 1:] + shift * occupied / (r / R)
+    mask = grid_mask.to(grid.device)[0] if r >= R else grid_mask.to(grid.device)[0, :, :r, :r, :r]
+    grid = grid * mask
+    if R - r > 0:
+        grid = F.pad(grid, (0, R - r, 0, R - r, 0, R - r, 0, 0, 0, 0))
+    return grid
+

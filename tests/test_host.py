@@ -204,6 +204,61 @@ def test_dataset_items_match_reference_golden(tmp_path):
     assert np.array_equal(ds[0].numpy(), gold["items"][0])
 
 
+def test_on_device_augmentation_matches_items(tmp_path):
+    """augment_on_device (the batched form of the loader's aug pipeline) == the reference golden items when it is handed the
+    same per-item jitter draws."""
+    from meshdiffusion_b200.dataset.shapenet_dmtet_dataset import augment_on_device
+    gold = np.load(os.path.join(GOLD, "dataset_items.npz"))
+    keep = [i for i in range(len(gold["raw"])) if i in set(int(v) for v in gold["filter"])]
+    raw = torch.tensor(gold["raw"][keep])
+    shifts = []
+    for i in range(len(keep)):
+        torch.manual_seed(100 + i)
+        shifts.append(torch.rand(3))
+    out = augment_on_device(raw, torch.tensor(gold["mask"]), torch.stack(shifts))
+    assert np.array_equal(out.numpy(), gold["items"][len(keep):]), "batched augmentation differs from the reference items"
+
+
+def test_partial_dmtet_and_grid_producers():
+    """geometry/formats.py against the reference's own code: data/tets_to_3dgrid.py::tet_to_grids exec'd from source, and the
+    fit_singleview.py:798-827 visibility tail restated literally."""
+    from meshdiffusion_b200.geometry import dmtet, formats
+    ref_root = "/root/reference"
+    verts, idx = dmtet.load_tet_grid(64)
+    coords = dmtet.grid_coords_of_tet_vertices(verts)
+    g = torch.Generator().manual_seed(3)
+    Nv, Fn = verts.shape[0], idx.shape[0]
+    sdf = torch.sign(torch.randn(Nv, generator=g))
+    deform = torch.randn(Nv, 3, generator=g) * 0.1
+    grid = formats.tets_to_3dgrid(coords, sdf, deform, 64)
+    assert grid.shape == (4, 64, 64, 64)
+    x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+    assert torch.equal(grid[0, x, y, z], sdf) and torch.equal(grid[1:, x, y, z], deform.t())
+    assert torch.equal(grid.abs().sum(0) != 0, dmtet.grid_mask_from_tets(64) == 1)  # sdf is +-1 on every tet vertex
+    if os.path.exists(os.path.join(ref_root, "data/tets_to_3dgrid.py")):  # authoring container: the reference function itself
+        src = open(os.path.join(ref_root, "data/tets_to_3dgrid.py")).read().split("if __name__")[0]
+        ns = {}
+        exec(src, ns)
+        want = ns["tet_to_grids"](coords, (sdf.unsqueeze(-1), deform), 64)
+        assert torch.equal(grid, want)
+    # visibility -> dmtet.pt
+    vis_id = torch.randperm(Fn, generator=g)[:5000]
+    rast_id = torch.randperm(Fn, generator=g)[:300]
+    d = formats.partial_dmtet_from_visibility(torch.tensor(idx), Nv, sdf, deform, vis_id, rast_id)
+    assert set(d) == {"sdf", "deform", "vis", "vis_rast"} and d["vis"].dtype == torch.float32 and d["vis_rast"].dtype == torch.bool
+    tets = torch.tensor(idx).long()
+    visible = torch.zeros(Fn)
+    visible[vis_id] = 1
+    both = visible.clone()
+    both[rast_id.unique()] = 1
+    want_vis = torch.zeros(Nv)
+    want_vis[tets[visible == 1].unique()] = 1
+    want_vr = want_vis.clone()
+    want_vr[tets[both == 1].unique()] = 1
+    assert torch.equal(d["vis"], want_vis) and torch.equal(d["vis_rast"], want_vr.bool())
+    assert d["vis_rast"].sum() >= d["vis"].sum() > 0
+
+
 def test_statistics_record_round_trip():
     """The split fixed-point (lo, hi) GroupNorm statistics record (csrc/gn_stats.cuh) as the Python mirror encodes it:
     exact round trip over 20 orders of magnitude, lo within +-2^15 * 2^24, far beyond the 5.5e11 single-word range."""
