@@ -460,6 +460,14 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
     const int btile = block_n * kRowBytes / (pair ? 2 : 1);
     const int max_stage = pair ? (2 * 128 * kRowBytes + 2 * 64 * kRowBytes) : (kAStageBytes + 3 * 128 * kRowBytes);
     const bool x3pair = pair && prec == kBF16X3;
+    {
+      // two M-tiles per CTA (weight tiles shared by both): bf16 / tf32 pair kernels with packed weights and enough tiles to
+      // fill every pair with 4-tile work items; MDB_M2=0 switches it off
+      const char* e = getenv("MDB_M2");
+      const int tiles_m = p.tx * p.ty * p.tz * p.tb;
+      m2 = pair && prec != kBF16X3 && !b_from_act && block_n == 128 && !(e && e[0] == '0') &&
+           (long long)tiles_m * p.n_tiles_n >= 4LL * (sm_count_or_default() / 2);
+    }
     stage_need = 0;
     p.n_segs = 0;
     auto push = [&](int n_groups, int epg, const LoadEntry& e, int couple) {
@@ -471,8 +479,8 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
       sg.a_stride = (sg.a_bytes + 1023) / 1024 * 1024;
       sg.jbytes = e.jrows * kRowBytes;
       sg.x3pair = couple;
-      const int need = epg * (sg.a_stride + e.nk * btile);
-      if (need > max_stage) throw std::runtime_error("mdb: pipeline group exceeds the stage size");
+      const int need = m2 ? 2 * sg.a_stride + e.nk * btile : epg * (sg.a_stride + e.nk * btile);
+      if (need > (m2 ? kMaxDynSmem / 2 : max_stage)) throw std::runtime_error("mdb: pipeline group exceeds the stage size");
       if (need > stage_need) stage_need = need;
       p.segs[p.n_segs++] = sg;
       p.total_groups += n_groups;
@@ -486,6 +494,8 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
       if (x3pair) {
         if (run % 2 != 0) throw std::runtime_error("mdb: X3 stage couples need an even run of entries");
         push(run, 1, loads[i], 1);
+      } else if (m2) {
+        push(run, 1, loads[i], 0);  // one entry per group: its box for both sub-tiles + the shared weight tiles
       } else if (loads[i].nk == 1 && 2 * (loads[i].rows * kRowBytes + btile) <= max_stage) {
         push(run / 2, 2, loads[i], 0);
         push(run % 2, 1, loads[i], 0);
@@ -508,10 +518,10 @@ void GemmOp::finalize(cudaStream_t stream, bool pack) {
   MDB_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
-template <int BN, bool TF32, bool CG2, bool GNB = false, bool X3 = false>
+template <int BN, bool TF32, bool CG2, bool GNB = false, bool X3 = false, bool M2 = false>
 static void launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured[64] = {};  // the attribute is per device
-  auto kern = gemm_tc_kernel<BN, TF32, CG2, GNB, X3>;
+  auto kern = gemm_tc_kernel<BN, TF32, CG2, GNB, X3, M2>;
   const int smem = GemmCfg<BN, CG2>::kFixedBytes + p.n_stages * p.stage_bytes;
   int dev = 0;
   MDB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -563,9 +573,10 @@ void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
     if (tf || p.splits > 1) throw std::runtime_error("mdb: GroupNorm-backward epilogue: bf16, no split-K");
     p.gnb_drop_thresh = rt_drop_thresh; p.gnb_drop_scale = rt_drop_scale; p.gnb_seed = rt_seed;
     if (pair) {
-      const int work = ((tiles_m + 1) / 2) * p.n_tiles_n;
+      const int work = (m2 ? (tiles_m + 3) / 4 : (tiles_m + 1) / 2) * p.n_tiles_n;
       const int pairs = sm_count() / 2;
-      launch_impl<128, false, true, true>(p, 2 * (work < pairs ? work : pairs), stream);
+      if (m2) launch_impl<128, false, true, true, false, true>(p, 2 * (work < pairs ? work : pairs), stream);
+      else launch_impl<128, false, true, true>(p, 2 * (work < pairs ? work : pairs), stream);
     } else {
       const int total = tiles_m * p.n_tiles_n;
       const int grid = total < sm_count() ? total : sm_count();
@@ -575,10 +586,11 @@ void GemmOp::launch(cudaStream_t stream, int B, void* out_override) const {
   }
   const bool x3 = prec == kBF16X3;
   if (pair) {
-    const int work = ((tiles_m + 1) / 2) * p.n_tiles_n;
+    const int work = (m2 ? (tiles_m + 3) / 4 : (tiles_m + 1) / 2) * p.n_tiles_n;
     const int pairs = sm_count() / 2;
     const int grid = 2 * (work < pairs ? work : pairs);
-    if (tf) launch_impl<128, true, true>(p, grid, stream);
+    if (m2) { if (tf) launch_impl<128, true, true, false, false, true>(p, grid, stream); else launch_impl<128, false, true, false, false, true>(p, grid, stream); }
+    else if (tf) launch_impl<128, true, true>(p, grid, stream);
     else if (x3) launch_impl<128, false, true, false, true>(p, grid, stream);
     else launch_impl<128, false, true>(p, grid, stream);
     return;

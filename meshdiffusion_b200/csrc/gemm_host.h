@@ -64,6 +64,7 @@ class GemmOp {
   Precision prec = kBF16;
   int block_n = 128;
   bool pair = false;  // CTA-pair kernel (cta_group::2)
+  bool m2 = false;    // pair kernel with two M-tiles per CTA sharing the staged weight tiles (decided by finalize)
   int splits = 1;     // split-K factor (small problems: few tiles, long K)
   std::vector<LoadEntry> loads;
   std::vector<WSrc> wsrcs;

@@ -239,9 +239,14 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 // code and register allocation are untouched.
 // X3: split-bf16 operands (see Precision::kBF16X3): the main loop is unchanged (the three partial products are extra
 // k-steps of the load table); the epilogue reads residuals and stores outputs as (hi, lo) bf16 pairs.
-template <int BLOCK_N, bool TF32, bool CG2, bool GNB = false, bool X3 = false>
+// M2 (CTA pairs, bf16 / tf32): every CTA owns TWO M-tiles per work item, multiplied against the SAME staged weight tiles
+// (four TMEM accumulators: 2 sub-tiles x 2 stages). The kernel is bounded by operand bytes crossing L2 -> SMEM per MMA
+// (ncu: profiles/r02_ncu_conv_*.txt); sharing the weight tiles between two A boxes cuts them from 3.5 KB to 2.5 KB.
+template <int BLOCK_N, bool TF32, bool CG2, bool GNB = false, bool X3 = false, bool M2 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, CG2>;
+  static_assert(!M2 || (CG2 && !X3 && BLOCK_N == 128), "M2 is built for 128-column CTA-pair kernels");
+  constexpr int kSubs = M2 ? 2 : 1;
   const int NS = p.n_stages;
   const uint32_t kStageBytesRt = (uint32_t)p.stage_bytes;
   extern __shared__ uint8_t smem_raw[];
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   const int tiles_m = p.tx * p.ty * p.tz * p.tb;
   // work items: (M-tile, N-tile) for a single CTA, (pair of adjacent M-tiles, N-tile) for a CTA pair
   const int splits = (!CG2 && p.splits > 1) ? p.splits : 1;
-  const int total_tiles = (CG2 ? (tiles_m + 1) / 2 : tiles_m) * p.n_tiles_n * splits;
+  const int total_tiles = (M2 ? (tiles_m + 3) / 4 : CG2 ? (tiles_m + 1) / 2 : tiles_m) * p.n_tiles_n * splits;
   const int first_tile = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
@@ -295,11 +300,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     hi = (int)((long long)p.total_groups * (sidx + 1) / splits);
   };
   int mt_of_tile = 0;  // M-tile index of the last decoded work item (GNB partial rows)
-  auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0) {
+  auto decode = [&](int tile, int& x0, int& y0, int& z0, int& b0, int& n0, int sub = 0) {
     tile /= splits;
     int nt = tile % p.n_tiles_n;
     int mt = tile / p.n_tiles_n;
-    if (CG2) mt = 2 * mt + (int)rank;
+    if (M2) mt = 4 * mt + 2 * (int)rank + sub;
+    else if (CG2) mt = 2 * mt + (int)rank;
     mt_of_tile = mt;
     n0 = nt * BLOCK_N;
     if (mt >= tiles_m) {  // odd tile count: the pair's second CTA gets an empty tile (all loads zero-filled, no stores)
@@ -321,6 +327,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       int x0, y0, z0, b0, n0;
       decode(tile, x0, y0, z0, b0, n0);
+      int x1 = 0, y1 = 0, z1 = 0, b1 = 0;
+      if constexpr (M2) { int n1; decode(tile, x1, y1, z1, b1, n1, 1); }
       int kcol = 0, l = 0, gi = 0, g_lo, g_hi;
       split_range(tile, g_lo, g_hi);
       const int bcoord = p.b_batched ? b0 : 0;
@@ -345,8 +353,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             if constexpr (CG2) {
               // both CTAs credit the LEADER's full barrier; only the leader arms it (with the pair's total bytes)
               const uint32_t bar = mapa_u32(full + 8 * st, 0);
-              if (rank == 0) mbar_expect_tx(full + 8 * st, 2 * group_bytes);
               const int nh = n0 + (int)rank * (BLOCK_N / 2);
+              if constexpr (M2) {
+                // one entry per group: its A box for both sub-tiles, then the weight tiles they share
+                if (rank == 0) mbar_expect_tx(full + 8 * st, 2 * (2 * seg.a_bytes + seg.nk * Cfg::kBTileBytes));
+                const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw0);
+                tma_load_5d_cg2(&p.amap[en.tmap], bar, sbase, en.c0, x0 + en.dx, y0 + en.dy, z0 + en.dz, b0);
+                tma_load_5d_cg2(&p.amap[en.tmap], bar, sbase + seg.a_stride, en.c0, x1 + en.dx, y1 + en.dy, z1 + en.dz, b1);
+                for (int j = 0; j < seg.nk; ++j) {
+                  tma_load_3d_cg2(&p.bmap, bar, sbase + 2 * seg.a_stride + j * Cfg::kBTileBytes, kc, nh, bcoord);
+                  kc += p.kb_elems;
+                }
+              } else {
+              if (rank == 0) mbar_expect_tx(full + 8 * st, 2 * group_bytes);
               for (int e = 0; e < seg.epg; ++e) {
                 const uint4 raw = e == 0 ? raw0 : raw1;
                 const LoadEntry& en = reinterpret_cast<const LoadEntry&>(raw);
@@ -356,6 +375,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
                   tma_load_3d_cg2(&p.bmap, bar, sbase + b_base + (e * seg.nk + j) * Cfg::kBTileBytes, kc, nh, bcoord);
                   kc += p.kb_elems;
                 }
+              }
               }
             } else {
               const uint32_t bar = full + 8 * st;
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(t_empty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * kSubs * BLOCK_N;
       uint32_t accumulate = 0;
       int gi = 0, g_lo, g_hi;
       split_range(tile, g_lo, g_hi);
@@ -442,6 +462,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sbase = stage0 + st * kStageBytesRt;
+            if constexpr (M2) {
+              for (int j = 0; j < seg.nk; ++j) {
+                const uint32_t b_lo = desc_lo(sbase + 2 * seg.a_stride + j * Cfg::kBTileBytes);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                  const uint32_t a_lo = desc_lo(sbase + sub * seg.a_stride + j * seg.jbytes);
+#pragma unroll
+                  for (int k = 0; k < kRowBytes / 32; ++k)
+                    umma_lo_cg2<TF32>(d_tmem + sub * BLOCK_N, a_lo + 2 * k, b_lo + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                }
+                accumulate = 1;
+              }
+            } else
             for (int e = 0; e < seg.epg; ++e) {
               for (int j = 0; j < seg.nk; ++j) {
                 const uint32_t a_lo = desc_lo(sbase + e * seg.a_stride + j * seg.jbytes);
@@ -480,8 +513,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+     for (int sub = 0; sub < kSubs; ++sub) {  // M2: the work item's two sub-tiles, one after the other
+      const int vit = it * kSubs + sub;
+      const bool last_sub = sub == kSubs - 1;
       int x0, y0, z0, b0, n0;
-      decode(tile, x0, y0, z0, b0, n0);
+      decode(tile, x0, y0, z0, b0, n0, sub);
       int r = row;
       const int xl = r % p.bx; r /= p.bx;
       const int yl = r % p.by; r /= p.by;
@@ -511,7 +547,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         named_bar_sync(1, kEpiThreads);
       }
       const float* s_bias = s_stats + 16 * BLOCK_N + bias_buf * 4 * BLOCK_N;
-      float* s_part = s_stats + (it & 1) * 8 * BLOCK_N;  // column partials, double-buffered across tiles
+      float* s_part = s_stats + (vit & 1) * 8 * BLOCK_N;  // column partials, double-buffered across (sub-)tiles
       // residual rows do not depend on the accumulator: fetch the first chunk while waiting for the MMAs, and every
       // next chunk while the current one is being stored, so the (L2/HBM) latency is never exposed
       uint4 rbuf[8];
@@ -548,10 +584,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (active) prefetch_res(ch0);
       mbar_wait(t_full + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * kSubs + sub) * BLOCK_N;
 
 #pragma unroll 1
-      if (!active) {  // nothing to drain for this warp: still release its share of the TMEM stage
+      if (!active && last_sub) {  // nothing to drain for this warp: still release its share of the TMEM stage
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if constexpr (CG2) { if (p.dbg_flags & 1) mbar_arrive_cluster_release(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); } else mbar_arrive(t_empty + 8 * acc); }
@@ -560,8 +596,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         uint32_t rr[32];
         tmem_ld32(t_row + ch * 32, rr);
         tmem_ld_wait();
-        if (ch + kChunkStep >= kChunks) {
-          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+        if (ch + kChunkStep >= kChunks && last_sub) {
+          // accumulator(s) fully drained into registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if constexpr (CG2) { if (p.dbg_flags & 1) mbar_arrive_cluster_release(mapa_u32(t_empty + 8 * acc, 0)); else mbar_arrive_cluster(mapa_u32(t_empty + 8 * acc, 0)); } else mbar_arrive(t_empty + 8 * acc); }
@@ -772,6 +808,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
           }
         }
       }
+     }  // sub
     }
   }
 

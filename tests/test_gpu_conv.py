@@ -34,6 +34,8 @@ CASES = [
     (1, 128, 4, 16, 3, 1),     # head (N=4 -> BLOCK_N 32, scalar stores)
     (1, 128, 4, 32, 5, 1),     # res128 head, 5-tap reuse
     (1, 128, 128, 32, 3, 1),
+    (3, 128, 128, 32, 3, 1),   # 768 M-tiles: CTA pairs with two M-tiles per CTA sharing the weight tiles (bf16 / tf32), odd batch
+    (2, 256, 128, 32, 3, 1),
 ]
 
 
