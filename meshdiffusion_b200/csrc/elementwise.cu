@@ -26,8 +26,15 @@ __device__ __forceinline__ float round_tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-// x * sigmoid(x) with a reciprocal instead of the full-precision division (8+ instructions): ex2.approx + rcp.rn, ~2 ulp
-__device__ __forceinline__ float silu_f(float x) { return x * __frcp_rn(1.f + __expf(-x)); }
+// x * sigmoid(x) = x / (1 + 2^(-x log2 e)) in five instructions: ex2.approx + rcp.approx (each ~1 ulp; the IEEE division and
+// __frcp_rn expand to a MUFU plus Newton steps -- ncu showed the bf16x3 GroupNorm pass issue-bound at 32 instructions per
+// element with them, profiles/r02_ncu_norm_act_x3.txt)
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
 // x*sigmoid(x) = 0.5x(1 + tanh(x/2)) with the single-MUFU tanh.approx (rel. error 2^-11: below bf16 resolution);
 // halves the MUFU pressure of the bf16 GroupNorm+SiLU pass, which otherwise co-limits with HBM bandwidth.
 __device__ __forceinline__ float silu_fast(float x) {
@@ -79,7 +86,7 @@ void launch_gn_finalize(const GnFinalizeArgs& a, int B, cudaStream_t s) {
 // MODE: 0 = bf16, 1 = tf32 (fp32 storage), 2 = split bf16 (X3: a channel vector is a 16-byte hi part and a 16-byte lo
 // part one logical row apart, on the input as on the output)
 template <int MODE>
-__global__ void __launch_bounds__(256) norm_act_kernel(NormActArgs a, int cv, int k) {
+__global__ void __launch_bounds__(256, MODE == 1 ? 4 : 3) norm_act_kernel(NormActArgs a, int cv, int k) {
   constexpr bool TF32 = MODE == 1;
   constexpr bool X3 = MODE == 2;
   constexpr int VEC = TF32 ? 4 : 8;  // 16 bytes
