@@ -572,11 +572,13 @@ void UNet::build() {
   stats_doubles_ = stats_cursor_;
   if (train_) {
     // emit the backward plan: the emitters recorded during the forward pass, in reverse order
+    bwd_count_ = 0;
     for (auto it = tape_.rbegin(); it != tape_.rend(); ++it) {
       touched_.clear();
       (*it)();
-      // every gradient this emitter writes is final once all of its launches have run
-      if (!dry_) for (auto& n : touched_) grad_ready_[n] = (int)bwd_steps_.size();
+      // every gradient this emitter writes is final once all of its launches have run (the dry pass counts the same
+      // launches, so a GPU-less plan answers mdb_unet_grad_ready too)
+      for (auto& n : touched_) grad_ready_[n] = bwd_count_;
     }
     tape_.clear();
     if (arena_.in_use() != 0) throw std::runtime_error("mdb: training plan leaked " + std::to_string(arena_.in_use()) + " arena bytes");
@@ -593,6 +595,10 @@ UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(precision_fr
   build();
   // allocate everything the dry run sized
   arena_bytes_ = arena_.peak();
+  {
+    long long off = 0;
+    for (auto& p : params_) { goff_[p.name] = off; off += p.numel; }
+  }
   if (dry_only) return;
   arena_base_ = (char*)dmalloc(arena_bytes_, false);
   stats_base_ = (long long*)dmalloc(stats_doubles_ * sizeof(long long));
@@ -604,10 +610,6 @@ UNet::UNet(const UNetConfig& cfg, bool dry_only) : cfg_(cfg), prec_(precision_fr
   if (train_) d_dense_out_ = (float*)dmalloc((size_t)cfg_.max_batch * dense_total_ * 4);
   for (auto& p : params_)
     if (!p.external) p.d = (float*)dmalloc(p.numel * 4);
-  {
-    long long off = 0;
-    for (auto& p : params_) { goff_[p.name] = off; off += p.numel; }
-  }
   dry_ = false;
   build();
   for (auto& g : gemms_) flops_ += g->flops;

@@ -176,7 +176,8 @@ class UNet {
   float* rt_grads_ = nullptr; const float* rt_dout_ = nullptr; bool rt_accum_ = false;
   int rt_drop_thresh_ = 0; float rt_drop_scale_ = 1.f; unsigned long long rt_seed_ = 0;
   float* d_dense_out_ = nullptr;  // [mb][dense_total] gradient of the time-embedding projections
-  void add_bwd(const std::string& name, std::function<void(cudaStream_t, int)> fn) { if (!dry_) bwd_steps_.push_back({name, fn}); }
+  int bwd_count_ = 0;  // launches of the backward plan emitted so far (counted in the dry pass too)
+  void add_bwd(const std::string& name, std::function<void(cudaStream_t, int)> fn) { ++bwd_count_; if (!dry_) bwd_steps_.push_back({name, fn}); }
   void free_act(const TensP& t);
   GradView new_grad(int C, int R);
   GradView grad_view(const GradView& g, int c0, int C);

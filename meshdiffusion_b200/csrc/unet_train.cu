@@ -52,10 +52,10 @@ Act UNet::act_of_grad(const GradView& g, int R) const {
 }
 
 long long UNet::G(const std::string& name) const {
+  touched_.push_back(name);
   if (dry_) return 0;
   auto it = goff_.find(name);
   if (it == goff_.end()) throw std::runtime_error("mdb: no gradient slot for " + name);
-  touched_.push_back(name);
   return it->second;
 }
 int UNet::grad_ready_step(const std::string& name) const {

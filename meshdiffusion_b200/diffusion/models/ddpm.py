@@ -78,6 +78,23 @@ def variance_scaling_uniform(shape, scale=1.0, generator=None):
     return (torch.rand(shape, generator=generator) * 2.0 - 1.0) * bound
 
 
+def make_grad_buckets(entries, total_numel, bucket_bytes):
+    """entries: (offset, numel, ready_launches) of every slot of the flat gradient buffer. Returns [(ready, lo, hi)] sorted
+    by readiness: contiguous, disjoint ranges that tile [0, total_numel), cut from the END of the buffer (the head's
+    gradients are final first, the time-embedding MLP's last) in pieces of at least `bucket_bytes`; a range is ready once
+    every gradient inside it is final."""
+    buckets, hi, ready = [], total_numel, 0
+    for off, numel, rdy in sorted(entries, reverse=True):
+        ready = max(ready, rdy)
+        if (hi - off) * 4 >= bucket_bytes:
+            buckets.append((ready, off, hi))
+            hi, ready = off, 0
+    if hi > 0:
+        buckets.append((ready, 0, hi))
+    buckets.sort()
+    return buckets
+
+
 class _ScoreNetFn(torch.autograd.Function):
     """Autograd node of the whole score network: forward and backward both run inside the native engine, so the stock
     `loss.backward()` of the reference's step_fn (losses.py:104-139) works unchanged. Parameter gradients are written
@@ -235,18 +252,8 @@ class ScoreNet(nn.Module):
             _native.check(L.mdb_unet_grad_offset(self._train_handle, n.encode(), ctypes.byref(off)))
             _native.check(L.mdb_unet_grad_ready(self._train_handle, n.encode(), ctypes.byref(rdy)))
             entries.append((off.value, self._param(n).numel(), rdy.value))
-        entries.sort(reverse=True)
-        buckets, hi, ready, lo = [], self._flat_grad.numel(), 0, self._flat_grad.numel()
-        for off, numel, rdy in entries:
-            lo, ready = off, max(ready, rdy)
-            if (hi - lo) * 4 >= self.bucket_bytes:
-                buckets.append((ready, lo, hi))
-                hi, ready = lo, 0
-        if hi > 0:
-            buckets.append((ready, 0, hi))
-        buckets.sort()
-        self._buckets = buckets
-        return buckets
+        self._buckets = make_grad_buckets(entries, self._flat_grad.numel(), self.bucket_bytes)
+        return self._buckets
 
     def _backward_with_overlapped_allreduce(self, dout, B, accumulate):
         """mdb_unet_backward_marked + one NCCL all-reduce (mean) per bucket on a side stream, each starting as soon as the

@@ -174,6 +174,56 @@ def test_world_size_2_gradient_allreduce(tmp_path):
     assert r.stdout.count("TRAIN_RANK_OK") == 2
 
 
+GLOO_BUCKET_CHILD = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+from meshdiffusion_b200.diffusion.models.ddpm import make_grad_buckets
+# a flat gradient buffer laid out like the engine's: slots in forward order, readiness falling with the offset, one
+# late-ready slot at the front (the time-embedding MLP) and a never-written slot (ready 0) in the middle
+g = torch.Generator().manual_seed(7)
+numels = [int(v) for v in torch.randint(1, 5000, (60,), generator=g)]
+offs = [0]
+for n in numels[:-1]:
+    offs.append(offs[-1] + n)
+total = offs[-1] + numels[-1]
+ready = [300] + [290 - 4 * i for i in range(59)]
+ready[20] = 0
+buckets = make_grad_buckets(list(zip(offs, numels, ready)), total, 16000 * 4)
+# the ranges tile the buffer exactly, each at least one bucket size (except the remainder at the front)
+cover = sorted((lo, hi) for _, lo, hi in buckets)
+assert cover[0][0] == 0 and cover[-1][1] == total and all(a[1] == b[0] for a, b in zip(cover, cover[1:])), cover
+assert len(buckets) >= 4 and all(hi - lo >= 16000 for _, lo, hi in buckets if lo != 0)
+assert [b[0] for b in buckets] == sorted(b[0] for b in buckets)
+for rdy, lo, hi in buckets:  # a range is ready only when all of its slots are
+    assert rdy == max(r for o, n, r in zip(offs, numels, ready) if lo <= o < hi)
+assert buckets[-1][1] == 0 and buckets[-1][0] == 300  # the front range (late slot) goes last
+# bucket-by-bucket mean == whole-buffer mean
+flat = torch.randn(total, generator=torch.Generator().manual_seed(rank))
+whole = flat.clone()
+dist.all_reduce(whole); whole /= world
+for _, lo, hi in buckets:
+    dist.all_reduce(flat[lo:hi])
+flat /= world
+assert torch.equal(flat, whole)
+print("BUCKET_RANK_OK", rank)
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_world_size_2_bucketed_gradient_mean(tmp_path):
+    """The data-parallel exchange's host logic on CPU/gloo: make_grad_buckets tiles the flat buffer from its end in
+    readiness order, and reducing it bucket by bucket equals reducing it whole."""
+    script = os.path.join(tmp_path, "child_buckets.py")
+    open(script, "w").write(GLOO_BUCKET_CHILD)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29535", script],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("BUCKET_RANK_OK") == 2
+
+
 def test_dataset_items_match_reference_golden(tmp_path):
     """ShapeNetDMTetDataset: items bit-identical to the reference class on the committed synthetic shapes (filter list,
     sign quirk, seeded jitter augmentation, mask multiply, right padding); golden from the reference class itself."""
