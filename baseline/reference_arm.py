@@ -52,13 +52,18 @@ def load(device):
     # the reference's top-level packages are called `lib` and `configs`: give them a clean import context
     for name in [m for m in sys.modules if m == "configs" or m.startswith("configs.") or m == "lib" or m.startswith("lib.")]:
         del sys.modules[name]
-    sys.path.insert(0, REF)
+    # ... and keep this repository's own `configs` package (a regular package beats the reference's namespace packages
+    # wherever it sits on sys.path) out of the way while the reference's modules are imported
+    repo_root = os.path.dirname(HERE)
+    saved = list(sys.path)
+    sys.path[:] = [REF] + [q for q in saved if os.path.abspath(q or os.getcwd()) != repo_root]
     try:
         from lib.diffusion.models import ddpm_res64, layers, utils as mutils  # noqa: F401
         from lib.diffusion import sde_lib, sampling
         from configs import res64 as cfg64
     finally:
-        sys.path.remove(REF)
+        sys.path[:] = saved
+    assert os.path.abspath(cfg64.__file__).startswith(os.path.abspath(REF)), "the reference's configs must come from baseline/_ref"
     config = cfg64.get_config()
     config.device = torch.device(device)
     return dict(mutils=mutils, layers=layers, sde_lib=sde_lib, sampling=sampling), config
