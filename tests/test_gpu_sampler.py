@@ -63,6 +63,41 @@ def test_public_sampler_matches_reference_golden(precision):
     assert torch.all(out.cpu()[:, :, sd["mask"][0, 0] == 0] == 0), "samples must vanish outside the grid mask"
 
 
+def test_config1_full_res64_ten_steps_match_oracle():
+    """BASELINE configs[0] at its real size: res64, batch 1, the first 10 iterations of the N=1000 schedule through the public
+    sampling_fn (bf16x3), against the oracle's pc_sample_uncond evaluated in true fp32 on the same GPU with the same noise
+    stream: 1e-3, and zero outside the grid mask."""
+    from helpers import full_config
+    from meshdiffusion_b200.diffusion import sde_lib
+    from oracle import unet_oracle
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = full_config("res64", "bf16x3")
+    model, sd = build_model(cfg, "cuda:0", 5)
+    R, B, n_it = 64, 1, 10
+    sde = sde_lib.VPSDE(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda")
+    mask = sd["mask"].view(1, R, R, R).cuda()
+    fn = _sampling_fn(cfg, sde, B, R, mask, max_iters=n_it)
+    real = torch.randn_like
+    torch.randn_like = lambda t, **kw: torch.randn(t.shape).to(t.device)
+    try:
+        torch.manual_seed(91)
+        out, _ = fn(model)
+        torch.manual_seed(91)
+        osde = sampler_oracle.VPSDETables(cfg.model.beta_min, cfg.model.beta_max, cfg.model.num_scales, device="cuda")
+        sdg = {k: v.cuda() for k, v in sd.items()}
+        arch = unet_oracle.arch_from_config(cfg)
+        net = lambda x, t: unet_oracle.unet_forward(sdg, arch, x, t)
+        with torch.no_grad():
+            ref = sampler_oracle.pc_sample_uncond(osde, net, torch.randn(B, 4, R, R, R).cuda(), mask, torch.randn_like, n_iters=n_it)
+    finally:
+        torch.randn_like = real
+    err = rel_max(out, ref)
+    print(f"config 1 (res64, B=1, 10 iterations) bf16x3 vs fp32 oracle: max err / max ref {err:.3e}")
+    assert err < 1e-3
+    assert torch.all(out[:, :, sd["mask"][0, 0].cuda() == 0] == 0)
+
+
 @pytest.mark.parametrize("pred,corr", [("euler_maruyama", "none"), ("reverse_diffusion", "none"),
                                        ("ancestral_sampling", "langevin"), ("reverse_diffusion", "ald")])
 def test_other_predictors_and_correctors_match_reference_golden(pred, corr):
