@@ -186,3 +186,7 @@ def train(config):
             save_checkpoint(checkpoint_meta_dir, state)
         if step != 0 and step % config.training.snapshot_freq == 0 or step == num_train_steps:
             save_checkpoint(os.path.join(checkpoint_dir, f"checkpoint_{step}.pth"), state)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
