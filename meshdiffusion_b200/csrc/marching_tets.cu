@@ -7,9 +7,12 @@
 // sorted edge table of the tet grid built once in mdb_marching_tets_prepare:
 //     vertex id of edge e  =  exclusive prefix sum of crossing flags over the globally sorted edge table.
 // Faces follow the reference's order: all 1-triangle tets in tet order, then all 2-triangle tets in tet order.
-// Per call the work is: flag kernels + three exclusive scans + emit kernels; one thread per edge / tet with
-// coalesced table reads, all samples of a batch in one launch (blockIdx.y = sample). HBM-bound: ~7 MB / sample
-// at R=64 (tets 2.5 MB + tet->edge table 3.8 MB + sdf/pos 0.5 MB).
+// Per call the work is 7 kernels for the whole batch (blockIdx.y = sample): flags + tile sums of the edge and tet segments in
+// one grid, tile sums of the valid-vertex flags, one scan of all tile sums; then -- once the host has sized the outputs from
+// the counts -- three emitters that finish the exclusive scan of their segment inside each 2048-element tile and write
+// vertices / faces / valid vertices straight from it (no flag or scan array is kept except the 1-byte flags and the
+// edge -> vertex-id map the face emitter gathers from). ~7 MB / sample at R=64 (tets 2.5 MB + tet->edge table 3.8 MB +
+// sdf/pos 0.5 MB); the exact-size outputs of the reference API force one host read of the counts per batch.
 #include "../../include/meshdiff_b200.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,42 +40,120 @@ __constant__ int8_t c_num_tri[16] = {0, 1, 1, 2, 1, 2, 2, 1, 1, 2, 2, 1, 2, 1, 1
 
 struct Handle {
   int F = 0, Nv = 0, E = 0, max_batch = 0;
+  int tE = 0, tF = 0, tV = 0;  // scan tiles per segment (edges, tets, vertices)
   int* d_tets = nullptr;      // [F][4]
   int2* d_edges = nullptr;    // [E] sorted (a<b), lexicographic
   int* d_tet_edges = nullptr; // [F][6] edge ids in base_tet_edges order
   // per-call workspace (sized for max_batch)
-  uint32_t *d_eflag = nullptr, *d_escan = nullptr;   // [B][E]
-  uint32_t *d_t1 = nullptr, *d_t1scan = nullptr;     // [B][F] (ntri==1)
-  uint32_t *d_t2 = nullptr, *d_t2scan = nullptr;     // [B][F] (ntri==2)
-  uint32_t *d_vflag = nullptr, *d_vscan = nullptr;   // [B][Nv]
-  uint8_t* d_tetidx = nullptr;                       // [B][F]
-  uint32_t* d_partials = nullptr;                    // scan scratch
-  int* d_counts = nullptr;                           // [B][4]: nverts, n1, n2, nvalidverts
-  int* h_counts = nullptr;                           // pinned
+  uint8_t* d_eflag = nullptr;    // [B][E]  edge crosses the surface
+  uint32_t* d_escan = nullptr;   // [B][E]  vertex id of a crossing edge (exclusive prefix sum of eflag)
+  uint8_t* d_tetidx = nullptr;   // [B][F]  occupancy code of the tet (-> 0 / 1 / 2 triangles)
+  uint8_t* d_vflag = nullptr;    // [B][Nv] vertex belongs to a tet with >= 1 triangle
+  uint32_t* d_partials = nullptr;  // [B][tE + 2 tF + tV] tile sums -> exclusive tile offsets, segments (E | n1 | n2 | V)
+  int* d_counts = nullptr;       // [B][4]: nverts, n1, n2, nvalidverts
+  int* h_counts = nullptr;       // pinned
   int last_batch = 0;
 };
 
 constexpr int SCAN_TILE = 2048;   // elements per block (256 threads x 8)
 
-// ---------------------------------------------------------------- exclusive scan of uint32 rows (3 kernels)
-__global__ void scan_tile_sums(const uint32_t* __restrict__ in, uint32_t* __restrict__ partials, int n, int tiles) {
-  __shared__ uint32_t red[8];
-  const int row = blockIdx.y, tile = blockIdx.x;
-  const uint32_t* p = in + (size_t)row * n;
-  uint32_t s = 0;
-  const int base = tile * SCAN_TILE;
-  for (int i = threadIdx.x; i < SCAN_TILE; i += 256) { const int k = base + i; if (k < n) s += p[k]; }
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+// exclusive prefix of `v` over the 256 threads of a block (+ the block total in *total); sh: 9 words
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* sh, uint32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) sh[w] = inc;
   __syncthreads();
-  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += red[w]; partials[(size_t)row * tiles + tile] = t; }
+  if (threadIdx.x < 8) {
+    uint32_t x = sh[threadIdx.x], xi = x;
+    for (int o = 1; o < 8; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffu, xi, o); if ((int)threadIdx.x >= o) xi += t; }
+    sh[threadIdx.x] = xi - x;          // exclusive warp offsets
+    if (threadIdx.x == 7) sh[8] = xi;  // block total
+  }
+  __syncthreads();
+  const uint32_t ex = sh[w] + inc - v;
+  if (total) *total = sh[8];
+  __syncthreads();
+  return ex;
 }
-__global__ void scan_partials(uint32_t* partials, int tiles, int* totals, int total_slot, int slots) {
-  // one block per row; sequential chunks of 1024 with a running carry
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t t = 0;
+  if (threadIdx.x == 0) for (int w = 0; w < 8; ++w) t += sh[w];
+  __syncthreads();
+  return t;  // valid in thread 0
+}
+
+// ---------------------------------------------------------------- pass 1: flags + tile sums, one launch
+// blockIdx.x < tE: a tile of the sorted edge table (crossing flags); else a tile of tets (occupancy code, 1- / 2-triangle
+// counts, scatter of the valid-vertex flags). blockIdx.y = sample. occ = sdf > 0 (dmtet.py:107).
+__global__ void __launch_bounds__(256) mt_flags_kernel(const int2* __restrict__ edges, const int* __restrict__ tets,
+                                                      const float* __restrict__ sdf, uint8_t* __restrict__ eflag,
+                                                      uint8_t* __restrict__ tetidx, uint8_t* __restrict__ vflag,
+                                                      uint32_t* __restrict__ partials, int E, int F, int Nv, int tE, int tF, int tV) {
+  __shared__ uint32_t sh[9];
+  const int b = blockIdx.y;
+  const float* s = sdf + (size_t)b * Nv;
+  uint32_t* part = partials + (size_t)b * (tE + 2 * tF + tV);
+  if ((int)blockIdx.x < tE) {
+    const int base = blockIdx.x * SCAN_TILE;
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = base + i * 256 + threadIdx.x;
+      if (e < E) {
+        const int2 ab = __ldg(edges + e);
+        const uint32_t f = ((s[ab.x] > 0.f) != (s[ab.y] > 0.f)) ? 1u : 0u;
+        eflag[(size_t)b * E + e] = (uint8_t)f;
+        n += f;
+      }
+    }
+    const uint32_t t = block_sum(n, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+  } else {
+    const int tile = blockIdx.x - tE;
+    const int base = tile * SCAN_TILE;
+    uint8_t* vf = vflag + (size_t)b * Nv;
+    uint32_t n = 0;  // low 16 bits: 1-triangle tets, high 16 bits: 2-triangle tets
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = base + i * 256 + threadIdx.x;
+      if (t < F) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(tets) + t);
+        const int idx = (s[v.x] > 0.f ? 1 : 0) | (s[v.y] > 0.f ? 2 : 0) | (s[v.z] > 0.f ? 4 : 0) | (s[v.w] > 0.f ? 8 : 0);
+        const int nt = c_num_tri[idx];
+        tetidx[(size_t)b * F + t] = (uint8_t)idx;
+        n += (nt == 1 ? 1u : 0u) + (nt == 2 ? 0x10000u : 0u);
+        if (nt > 0) { vf[v.x] = 1; vf[v.y] = 1; vf[v.z] = 1; vf[v.w] = 1; }  // valid_vert_idx (dmtet.py:161)
+      }
+    }
+    const uint32_t t = block_sum(n, sh);
+    if (threadIdx.x == 0) { part[tE + tile] = t & 0xffffu; part[tE + tF + tile] = t >> 16; }
+  }
+}
+
+__global__ void __launch_bounds__(256) mt_vflag_sums_kernel(const uint8_t* __restrict__ vflag, uint32_t* __restrict__ partials,
+                                                           int Nv, int tE, int tF, int tV) {
+  __shared__ uint32_t sh[9];
+  const int b = blockIdx.y;
+  const int base = blockIdx.x * SCAN_TILE;
+  uint32_t n = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int v = base + i * 256 + threadIdx.x; if (v < Nv) n += vflag[(size_t)b * Nv + v]; }
+  const uint32_t t = block_sum(n, sh);
+  if (threadIdx.x == 0) partials[(size_t)b * (tE + 2 * tF + tV) + tE + 2 * tF + blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------- pass 2: exclusive scan of the tile sums, 4 segments per sample
+__global__ void __launch_bounds__(1024) mt_scan_partials_kernel(uint32_t* partials, int tE, int tF, int tV, int* counts) {
   __shared__ uint32_t sh[1024];
   __shared__ uint32_t carry;
-  const int row = blockIdx.x;
-  uint32_t* p = partials + (size_t)row * tiles;
+  const int seg = blockIdx.x, b = blockIdx.y;
+  const int tiles = seg == 0 ? tE : (seg == 3 ? tV : tF);
+  const int base0 = seg == 0 ? 0 : (seg == 1 ? tE : (seg == 2 ? tE + tF : tE + 2 * tF));
+  uint32_t* p = partials + (size_t)b * (tE + 2 * tF + tV) + base0;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int base = 0; base < tiles; base += 1024) {
@@ -81,7 +162,7 @@ __global__ void scan_partials(uint32_t* partials, int tiles, int* totals, int to
     sh[threadIdx.x] = v;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
-      uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      const uint32_t t = (int)threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
       __syncthreads();
       sh[threadIdx.x] += t;
       __syncthreads();
@@ -92,109 +173,84 @@ __global__ void scan_partials(uint32_t* partials, int tiles, int* totals, int to
     if (threadIdx.x == 1023) carry += incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0 && totals) totals[row * slots + total_slot] = (int)carry;
-}
-__global__ void scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ partials,
-                           int n, int tiles) {
-  __shared__ uint32_t sh[256];
-  const int row = blockIdx.y, tile = blockIdx.x;
-  const uint32_t* p = in + (size_t)row * n;
-  uint32_t* q = out + (size_t)row * n;
-  const int base = tile * SCAN_TILE + threadIdx.x * 8;
-  uint32_t v[8], s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { v[i] = (base + i < n) ? p[base + i] : 0; s += v[i]; }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 1; o < 256; o <<= 1) {
-    uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += t;
-    __syncthreads();
-  }
-  uint32_t run = partials[(size_t)row * tiles + tile] + sh[threadIdx.x] - s;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { if (base + i < n) q[base + i] = run; run += v[i]; }
+  if (threadIdx.x == 0) counts[b * 4 + seg] = (int)carry;
 }
 
-static void exclusive_scan_rows(const uint32_t* in, uint32_t* out, uint32_t* partials, int n, int rows, int* totals,
-                                int total_slot, int slots, cudaStream_t s) {
-  const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  scan_tile_sums<<<dim3(tiles, rows), 256, 0, s>>>(in, partials, n, tiles);
-  scan_partials<<<rows, 1024, 0, s>>>(partials, tiles, totals, total_slot, slots);
-  scan_apply<<<dim3(tiles, rows), 256, 0, s>>>(in, out, partials, n, tiles);
-}
-
-// ---------------------------------------------------------------- per-sample kernels
-__global__ void edge_flags_kernel(const int2* __restrict__ edges, const float* __restrict__ sdf, uint32_t* __restrict__ eflag,
-                                  int E, int Nv) {
-  const int b = blockIdx.y;
-  const float* s = sdf + (size_t)b * Nv;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    const int2 ab = edges[e];
-    eflag[(size_t)b * E + e] = ((s[ab.x] > 0.f) != (s[ab.y] > 0.f)) ? 1u : 0u;  // occ = sdf > 0 (dmtet.py:107)
-  }
-}
-
-__global__ void tet_flags_kernel(const int* __restrict__ tets, const float* __restrict__ sdf, uint8_t* __restrict__ tetidx,
-                                 uint32_t* __restrict__ t1, uint32_t* __restrict__ t2, uint32_t* __restrict__ vflag, int F, int Nv) {
-  const int b = blockIdx.y;
-  const float* s = sdf + (size_t)b * Nv;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < F; t += gridDim.x * blockDim.x) {
-    const int4 v = reinterpret_cast<const int4*>(tets)[t];
-    const int idx = (s[v.x] > 0.f ? 1 : 0) | (s[v.y] > 0.f ? 2 : 0) | (s[v.z] > 0.f ? 4 : 0) | (s[v.w] > 0.f ? 8 : 0);
-    const int nt = c_num_tri[idx];
-    tetidx[(size_t)b * F + t] = (uint8_t)idx;
-    t1[(size_t)b * F + t] = nt == 1;
-    t2[(size_t)b * F + t] = nt == 2;
-    if (nt > 0) {  // valid_vert_idx = unique(tets with >= 1 triangle) (dmtet.py:161)
-      uint32_t* vf = vflag + (size_t)b * Nv;
-      vf[v.x] = 1; vf[v.y] = 1; vf[v.z] = 1; vf[v.w] = 1;
-    }
-  }
-}
-
-// verts[vid] = (p_a * (-s_b) + p_b * s_a) / (s_a - s_b) in the reference's operation order (dmtet.py:125-132)
-__global__ void emit_verts_kernel(const int2* __restrict__ edges, const uint32_t* __restrict__ eflag,
-                                  const uint32_t* __restrict__ escan, const float* __restrict__ pos, long long pos_bstride,
-                                  const float* __restrict__ sdf, float* __restrict__ verts, const long long* __restrict__ vert_off,
-                                  int E, int Nv) {
+// ---------------------------------------------------------------- pass 3: in-tile scans fused with the emitters
+// verts[vid] = (p_a * (-s_b) + p_b * s_a) / (s_a - s_b) in the reference's operation order (dmtet.py:125-132);
+// vid = rank of the edge among the crossing edges of the sorted table. Also leaves escan for the face emitter.
+__global__ void __launch_bounds__(256) mt_emit_verts_kernel(const int2* __restrict__ edges, const uint8_t* __restrict__ eflag,
+                                                           const uint32_t* __restrict__ partials, uint32_t* __restrict__ escan,
+                                                           const float* __restrict__ pos, long long pos_bstride,
+                                                           const float* __restrict__ sdf, float* __restrict__ verts,
+                                                           const long long* __restrict__ vert_off, int E, int Nv, int ptiles) {
+  __shared__ uint32_t sh[9];
   const int b = blockIdx.y;
   const float* s = sdf + (size_t)b * Nv;
   const float* p = pos + (size_t)b * pos_bstride;
   float* out = verts + vert_off[b] * 3;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-    if (!eflag[(size_t)b * E + e]) continue;
-    const int2 ab = edges[e];
-    const float sa = s[ab.x], sb = -s[ab.y];
-    const float den = __fadd_rn(sa, sb);
-    const float wa = __fdiv_rn(sb, den), wb = __fdiv_rn(sa, den);  // flip: weight of a is (-s_b)/den
-    const uint32_t vid = escan[(size_t)b * E + e];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  uint8_t f[8];
+  uint32_t n = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      out[(size_t)vid * 3 + k] = __fadd_rn(__fmul_rn(p[(size_t)ab.x * 3 + k], wa), __fmul_rn(p[(size_t)ab.y * 3 + k], wb));
+  for (int i = 0; i < 8; ++i) { f[i] = (base + i < E) ? eflag[(size_t)b * E + base + i] : 0; n += f[i]; }
+  uint32_t run = partials[(size_t)b * ptiles + blockIdx.x] + block_excl_scan(n, sh, nullptr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = base + i;
+    if (e >= E) break;
+    escan[(size_t)b * E + e] = run;
+    if (f[i]) {
+      const int2 ab = __ldg(edges + e);
+      const float sa = s[ab.x], sb = -s[ab.y];
+      const float den = __fadd_rn(sa, sb);
+      const float wa = __fdiv_rn(sb, den), wb = __fdiv_rn(sa, den);  // flip: weight of a is (-s_b)/den
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        out[(size_t)run * 3 + k] = __fadd_rn(__fmul_rn(p[(size_t)ab.x * 3 + k], wa), __fmul_rn(p[(size_t)ab.y * 3 + k], wb));
+      ++run;
+    }
   }
 }
 
-__global__ void emit_faces_kernel(const int* __restrict__ tet_edges, const uint8_t* __restrict__ tetidx,
-                                  const uint32_t* __restrict__ t1scan, const uint32_t* __restrict__ t2scan,
-                                  const uint32_t* __restrict__ escan, const int* __restrict__ counts,
-                                  long long* __restrict__ faces, long long* __restrict__ uv_idx, long long* __restrict__ f2t,
-                                  const long long* __restrict__ face_off, int F, int E) {
+// faces: all 1-triangle tets in tet order, then all 2-triangle tets in tet order (dmtet.py:136-144); uv_idx / face_to_tet
+// as map_uv (dmtet.py:70-99, 156-159)
+__global__ void __launch_bounds__(256) mt_emit_faces_kernel(const int* __restrict__ tet_edges, const uint8_t* __restrict__ tetidx,
+                                                           const uint32_t* __restrict__ partials, const uint32_t* __restrict__ escan,
+                                                           const int* __restrict__ counts, long long* __restrict__ faces,
+                                                           long long* __restrict__ uv_idx, long long* __restrict__ f2t,
+                                                           const long long* __restrict__ face_off, int F, int E, int tE, int tF,
+                                                           int ptiles) {
+  __shared__ uint32_t sh[9];
   const int b = blockIdx.y;
   const int n1 = counts[b * 4 + 1];
   long long* fo = faces + face_off[b] * 3;
   long long* uo = uv_idx + face_off[b] * 3;
   long long* to = f2t + face_off[b];
   const uint32_t* es = escan + (size_t)b * E;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < F; t += gridDim.x * blockDim.x) {
-    const int idx = tetidx[(size_t)b * F + t];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  uint8_t code[8];
+  uint32_t n = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    code[i] = (base + i < F) ? tetidx[(size_t)b * F + base + i] : 0;
+    const int nt = c_num_tri[code[i]];
+    n += (nt == 1 ? 1u : 0u) + (nt == 2 ? 0x10000u : 0u);
+  }
+  const uint32_t ex = block_excl_scan(n, sh, nullptr);
+  uint32_t r1 = partials[(size_t)b * ptiles + tE + blockIdx.x] + (ex & 0xffffu);
+  uint32_t r2 = partials[(size_t)b * ptiles + tE + tF + blockIdx.x] + (ex >> 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = base + i;
+    const int idx = code[i];
     const int nt = c_num_tri[idx];
     if (nt == 0) continue;
-    const long long f0 = nt == 1 ? (long long)t1scan[(size_t)b * F + t] : (long long)n1 + 2LL * t2scan[(size_t)b * F + t];
+    const long long f0 = nt == 1 ? (long long)r1 : (long long)n1 + 2LL * r2;
+    if (nt == 1) ++r1; else ++r2;
     int eid[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) eid[k] = tet_edges[(size_t)t * 6 + k];
+    for (int k = 0; k < 6; ++k) eid[k] = __ldg(tet_edges + (size_t)t * 6 + k);
     for (int j = 0; j < nt; ++j) {
       const long long f = f0 + j;
 #pragma unroll
@@ -208,12 +264,20 @@ __global__ void emit_faces_kernel(const int* __restrict__ tet_edges, const uint8
   }
 }
 
-__global__ void emit_valid_verts_kernel(const uint32_t* __restrict__ vflag, const uint32_t* __restrict__ vscan,
-                                        long long* __restrict__ out, const long long* __restrict__ vv_off, int Nv) {
+__global__ void __launch_bounds__(256) mt_emit_valid_verts_kernel(const uint8_t* __restrict__ vflag, const uint32_t* __restrict__ partials,
+                                                                 long long* __restrict__ out, const long long* __restrict__ vv_off,
+                                                                 int Nv, int tE, int tF, int ptiles) {
+  __shared__ uint32_t sh[9];
   const int b = blockIdx.y;
   long long* o = out + vv_off[b];
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Nv; v += gridDim.x * blockDim.x)
-    if (vflag[(size_t)b * Nv + v]) o[vscan[(size_t)b * Nv + v]] = v;
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  uint8_t f[8];
+  uint32_t n = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { f[i] = (base + i < Nv) ? vflag[(size_t)b * Nv + base + i] : 0; n += f[i]; }
+  uint32_t run = partials[(size_t)b * ptiles + tE + 2 * tF + blockIdx.x] + block_excl_scan(n, sh, nullptr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) if (f[i]) o[run++] = base + i;
 }
 
 static int grid1d(int n) { int g = (n + 255) / 256; return g > 148 * 4 ? 148 * 4 : (g < 1 ? 1 : g); }
@@ -280,13 +344,11 @@ int mdb_marching_tets_prepare(const int* tets_host, int F, int Nv, int max_batch
   MT_CHECK(cudaMemcpy(h->d_tets, tets_host, (size_t)F * 16, cudaMemcpyHostToDevice));
   MT_CHECK(cudaMemcpy(h->d_edges, edges.data(), (size_t)h->E * 8, cudaMemcpyHostToDevice));
   MT_CHECK(cudaMemcpy(h->d_tet_edges, te.data(), (size_t)F * 24, cudaMemcpyHostToDevice));
-  MT_CHECK(cudaMalloc(&h->d_eflag, B * h->E * 4)); MT_CHECK(cudaMalloc(&h->d_escan, B * h->E * 4));
-  MT_CHECK(cudaMalloc(&h->d_t1, B * F * 4)); MT_CHECK(cudaMalloc(&h->d_t1scan, B * F * 4));
-  MT_CHECK(cudaMalloc(&h->d_t2, B * F * 4)); MT_CHECK(cudaMalloc(&h->d_t2scan, B * F * 4));
-  MT_CHECK(cudaMalloc(&h->d_vflag, B * Nv * 4)); MT_CHECK(cudaMalloc(&h->d_vscan, B * Nv * 4));
+  h->tE = (h->E + SCAN_TILE - 1) / SCAN_TILE; h->tF = (F + SCAN_TILE - 1) / SCAN_TILE; h->tV = (Nv + SCAN_TILE - 1) / SCAN_TILE;
+  MT_CHECK(cudaMalloc(&h->d_eflag, B * h->E)); MT_CHECK(cudaMalloc(&h->d_escan, B * h->E * 4));
+  MT_CHECK(cudaMalloc(&h->d_vflag, B * Nv));
   MT_CHECK(cudaMalloc(&h->d_tetidx, B * F));
-  const int maxn = std::max(std::max(h->E, F), Nv);
-  MT_CHECK(cudaMalloc(&h->d_partials, B * ((maxn + SCAN_TILE - 1) / SCAN_TILE + 1) * 4));
+  MT_CHECK(cudaMalloc(&h->d_partials, B * (size_t)(h->tE + 2 * h->tF + h->tV) * 4));
   MT_CHECK(cudaMalloc(&h->d_counts, B * 4 * sizeof(int)));
   MT_CHECK(cudaMallocHost(&h->h_counts, B * 4 * sizeof(int)));
   *handle = h;
@@ -297,8 +359,7 @@ void mdb_marching_tets_destroy(void* handle) {
   auto* h = static_cast<Handle*>(handle);
   if (!h) return;
   cudaFree(h->d_tets); cudaFree(h->d_edges); cudaFree(h->d_tet_edges);
-  cudaFree(h->d_eflag); cudaFree(h->d_escan); cudaFree(h->d_t1); cudaFree(h->d_t1scan);
-  cudaFree(h->d_t2); cudaFree(h->d_t2scan); cudaFree(h->d_vflag); cudaFree(h->d_vscan);
+  cudaFree(h->d_eflag); cudaFree(h->d_escan); cudaFree(h->d_vflag);
   cudaFree(h->d_tetidx); cudaFree(h->d_partials); cudaFree(h->d_counts); cudaFreeHost(h->h_counts);
   delete h;
 }
@@ -328,13 +389,13 @@ int mdb_marching_tets_count(void* handle, const float* sdf, int batch, int* coun
   cudaStream_t s = (cudaStream_t)stream;
   if (batch < 1 || batch > h->max_batch) throw std::runtime_error("mdb MT: batch out of range");
   const int E = h->E, F = h->F, Nv = h->Nv;
-  MT_CHECK(cudaMemsetAsync(h->d_vflag, 0, (size_t)batch * Nv * 4, s));
-  edge_flags_kernel<<<dim3(grid1d(E), batch), 256, 0, s>>>(h->d_edges, sdf, h->d_eflag, E, Nv);
-  tet_flags_kernel<<<dim3(grid1d(F), batch), 256, 0, s>>>(h->d_tets, sdf, h->d_tetidx, h->d_t1, h->d_t2, h->d_vflag, F, Nv);
-  exclusive_scan_rows(h->d_eflag, h->d_escan, h->d_partials, E, batch, h->d_counts, 0, 4, s);
-  exclusive_scan_rows(h->d_t1, h->d_t1scan, h->d_partials, F, batch, h->d_counts, 1, 4, s);
-  exclusive_scan_rows(h->d_t2, h->d_t2scan, h->d_partials, F, batch, h->d_counts, 2, 4, s);
-  exclusive_scan_rows(h->d_vflag, h->d_vscan, h->d_partials, Nv, batch, h->d_counts, 3, 4, s);
+  // 4 launches: vertex-flag clear, flags + tile sums (edges and tets in one grid), vertex-flag tile sums (they depend on the
+  // tets' scatter), scan of the tile sums of all four segments
+  MT_CHECK(cudaMemsetAsync(h->d_vflag, 0, (size_t)batch * Nv, s));
+  mt_flags_kernel<<<dim3(h->tE + h->tF, batch), 256, 0, s>>>(h->d_edges, h->d_tets, sdf, h->d_eflag, h->d_tetidx, h->d_vflag,
+                                                             h->d_partials, E, F, Nv, h->tE, h->tF, h->tV);
+  mt_vflag_sums_kernel<<<dim3(h->tV, batch), 256, 0, s>>>(h->d_vflag, h->d_partials, Nv, h->tE, h->tF, h->tV);
+  mt_scan_partials_kernel<<<dim3(4, batch), 1024, 0, s>>>(h->d_partials, h->tE, h->tF, h->tV, h->d_counts);
   MT_CHECK(cudaGetLastError());
   MT_CHECK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)batch * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   MT_CHECK(cudaStreamSynchronize(s));
@@ -360,11 +421,13 @@ int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batc
   cudaStream_t s = (cudaStream_t)stream;
   if (batch != h->last_batch) throw std::runtime_error("mdb MT: call mdb_marching_tets_count first with the same batch");
   const int E = h->E, F = h->F, Nv = h->Nv;
-  emit_verts_kernel<<<dim3(grid1d(E), batch), 256, 0, s>>>(h->d_edges, h->d_eflag, h->d_escan, pos, pos_batch_stride, sdf,
-                                                           verts, vert_off, E, Nv);
-  emit_faces_kernel<<<dim3(grid1d(F), batch), 256, 0, s>>>(h->d_tet_edges, h->d_tetidx, h->d_t1scan, h->d_t2scan, h->d_escan,
-                                                           h->d_counts, faces, uv_idx, face_to_tet, face_off, F, E);
-  emit_valid_verts_kernel<<<dim3(grid1d(Nv), batch), 256, 0, s>>>(h->d_vflag, h->d_vscan, valid_vert_idx, vv_off, Nv);
+  // 3 launches: each finishes the exclusive scan of its segment inside the tile and emits straight from it
+  const int pt = h->tE + 2 * h->tF + h->tV;
+  mt_emit_verts_kernel<<<dim3(h->tE, batch), 256, 0, s>>>(h->d_edges, h->d_eflag, h->d_partials, h->d_escan, pos, pos_batch_stride,
+                                                          sdf, verts, vert_off, E, Nv, pt);
+  mt_emit_faces_kernel<<<dim3(h->tF, batch), 256, 0, s>>>(h->d_tet_edges, h->d_tetidx, h->d_partials, h->d_escan, h->d_counts, faces,
+                                                          uv_idx, face_to_tet, face_off, F, E, h->tE, h->tF, pt);
+  mt_emit_valid_verts_kernel<<<dim3(h->tV, batch), 256, 0, s>>>(h->d_vflag, h->d_partials, valid_vert_idx, vv_off, Nv, h->tE, h->tF, pt);
   MT_CHECK(cudaGetLastError());
   MT_API_END
 }
