@@ -122,7 +122,9 @@ class ScoreNet(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.arch = arch_from_config(config)
-        self.precision = str(config.model.get("compute_dtype", "tf32")) if hasattr(config.model, "get") else "tf32"
+        # inference operand mode; the default is the parity-grade one (results within 1e-3 of the reference's fp32 arithmetic).
+        # 'tf32' (1.6e-3, 1.55x faster) and 'bf16' (1.3e-2, 2.7x faster) are opt-in. Training always runs the bf16 plan.
+        self.precision = str(config.model.get("compute_dtype", "bf16x3")) if hasattr(config.model, "get") else "bf16x3"
         if self.precision not in PRECISIONS:
             raise ValueError("config.model.compute_dtype must be 'bf16', 'tf32' or 'bf16x3'")
         self.max_batch = int(config.model.get("engine_max_batch", 0) or 0) if hasattr(config.model, "get") else 0
