@@ -215,7 +215,8 @@ int mdb_marching_tets_uvs(void* handle, float* uvs, void* stream);
 /* Phase 1 (synchronises): sdf device fp32 [B][n_verts]; counts_host[b] = {n_verts_out, n_faces, n_valid_verts}. */
 int mdb_marching_tets_count(void* handle, const float* sdf, int batch, int* counts_host, void* stream);
 /* Phase 2: pos device fp32 [B][n_verts][3] (pos_batch_stride in floats; 0 = shared). Outputs packed per sample at
- * the given element offsets (device int64 [B]). */
+ * the given element offsets (device int64 [B]); NULL offsets = samples packed back to back in batch order (the exclusive
+ * sums of the phase-1 counts, which the library keeps on the device: no upload needed). */
 int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batch_stride, const float* sdf, int batch,
                               float* verts, long long* faces, long long* uv_idx, long long* face_to_tet,
                               long long* valid_vert_idx, const long long* vert_off, const long long* face_off,

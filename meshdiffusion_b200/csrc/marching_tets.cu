@@ -51,6 +51,7 @@ struct Handle {
   uint8_t* d_vflag = nullptr;    // [B][Nv] vertex belongs to a tet with >= 1 triangle
   uint32_t* d_partials = nullptr;  // [B][tE + 2 tF + tV] tile sums -> exclusive tile offsets, segments (E | n1 | n2 | V)
   int* d_counts = nullptr;       // [B][4]: nverts, n1, n2, nvalidverts
+  long long* d_offs = nullptr;   // [3][B]: packed output offsets of every sample (verts, faces, valid verts)
   int* h_counts = nullptr;       // pinned
   int last_batch = 0;
 };
@@ -174,6 +175,17 @@ __global__ void __launch_bounds__(1024) mt_scan_partials_kernel(uint32_t* partia
     __syncthreads();
   }
   if (threadIdx.x == 0) counts[b * 4 + seg] = (int)carry;
+}
+
+// packed output offsets of the batch: exclusive sums over the samples of (nverts, n1 + 2 n2, nvalidverts)
+__global__ void mt_offsets_kernel(const int* __restrict__ counts, long long* __restrict__ offs, int B, int stride) {
+  if (threadIdx.x < 3) {
+    long long run = 0;
+    for (int b = 0; b < B; ++b) {
+      offs[(size_t)threadIdx.x * stride + b] = run;
+      run += threadIdx.x == 0 ? counts[b * 4] : (threadIdx.x == 1 ? counts[b * 4 + 1] + 2 * counts[b * 4 + 2] : counts[b * 4 + 3]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------- pass 3: in-tile scans fused with the emitters
@@ -350,6 +362,7 @@ int mdb_marching_tets_prepare(const int* tets_host, int F, int Nv, int max_batch
   MT_CHECK(cudaMalloc(&h->d_tetidx, B * F));
   MT_CHECK(cudaMalloc(&h->d_partials, B * (size_t)(h->tE + 2 * h->tF + h->tV) * 4));
   MT_CHECK(cudaMalloc(&h->d_counts, B * 4 * sizeof(int)));
+  MT_CHECK(cudaMalloc(&h->d_offs, 3 * B * sizeof(long long)));
   MT_CHECK(cudaMallocHost(&h->h_counts, B * 4 * sizeof(int)));
   *handle = h;
   MT_API_END
@@ -360,7 +373,7 @@ void mdb_marching_tets_destroy(void* handle) {
   if (!h) return;
   cudaFree(h->d_tets); cudaFree(h->d_edges); cudaFree(h->d_tet_edges);
   cudaFree(h->d_eflag); cudaFree(h->d_escan); cudaFree(h->d_vflag);
-  cudaFree(h->d_tetidx); cudaFree(h->d_partials); cudaFree(h->d_counts); cudaFreeHost(h->h_counts);
+  cudaFree(h->d_tetidx); cudaFree(h->d_partials); cudaFree(h->d_counts); cudaFree(h->d_offs); cudaFreeHost(h->h_counts);
   delete h;
 }
 
@@ -396,6 +409,7 @@ int mdb_marching_tets_count(void* handle, const float* sdf, int batch, int* coun
                                                              h->d_partials, E, F, Nv, h->tE, h->tF, h->tV);
   mt_vflag_sums_kernel<<<dim3(h->tV, batch), 256, 0, s>>>(h->d_vflag, h->d_partials, Nv, h->tE, h->tF, h->tV);
   mt_scan_partials_kernel<<<dim3(4, batch), 1024, 0, s>>>(h->d_partials, h->tE, h->tF, h->tV, h->d_counts);
+  mt_offsets_kernel<<<1, 32, 0, s>>>(h->d_counts, h->d_offs, batch, h->max_batch);
   MT_CHECK(cudaGetLastError());
   MT_CHECK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)batch * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   MT_CHECK(cudaStreamSynchronize(s));
@@ -421,6 +435,10 @@ int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batc
   cudaStream_t s = (cudaStream_t)stream;
   if (batch != h->last_batch) throw std::runtime_error("mdb MT: call mdb_marching_tets_count first with the same batch");
   const int E = h->E, F = h->F, Nv = h->Nv;
+  // NULL offsets: outputs packed back to back in sample order -- the offsets the count pass left on the device
+  if (!vert_off) vert_off = h->d_offs;
+  if (!face_off) face_off = h->d_offs + h->max_batch;
+  if (!vv_off) vv_off = h->d_offs + 2 * (size_t)h->max_batch;
   // 3 launches: each finishes the exclusive scan of its segment inside the tile and emits straight from it
   const int pt = h->tE + 2 * h->tF + h->tV;
   mt_emit_verts_kernel<<<dim3(h->tE, batch), 256, 0, s>>>(h->d_edges, h->d_eflag, h->d_partials, h->d_escan, pos, pos_batch_stride,

@@ -93,10 +93,10 @@ class MarchingTets:
         uv_idx = torch.empty_like(faces)
         f2t = torch.empty(int(off[-1, 1]), device=dev, dtype=torch.int64)
         vvi = torch.empty(int(off[-1, 2]), device=dev, dtype=torch.int64)
-        offs = torch.tensor(off[:-1].T.copy(), device=dev, dtype=torch.int64).contiguous()  # [3][B]
+        # outputs are packed back to back in batch order: the library already holds those offsets on the device (NULL)
         _native.check(L.mdb_marching_tets_extract(self._h, _native.ptr(pos), stride, _native.ptr(sdf), B, _native.ptr(verts),
                                                   _native.ptr(faces), _native.ptr(uv_idx), _native.ptr(f2t), _native.ptr(vvi),
-                                                  _native.ptr(offs[0]), _native.ptr(offs[1]), _native.ptr(offs[2]), stream))
+                                                  None, None, None, stream))
         uvs = self.uvs(dev)
         out = []
         for b in range(B):

@@ -62,6 +62,23 @@ def test_marching_tets_oracle_matches_reference_golden():
         assert tuple(uvs.shape) == tuple(gold[case + "_uvs_shape"])
 
 
+def test_marching_tets_oracle_matches_reference_golden_128():
+    """The R=128 grid (1.39 M tets): the oracle's integer outputs hash to the digests the REFERENCE DMTet class produced."""
+    import hashlib
+    from meshdiffusion_b200.geometry import dmtet
+    gold = load_golden("marching_tets_128.npz")
+    verts, idx = dmtet.load_tet_grid(128)
+    sdf, pos = synth.synthetic_dmtet(verts, seed=0, noisy=False, res=128)
+    out = mt_oracle.marching_tets(pos, sdf, idx)
+    for n, a in zip(["verts", "faces", "uvs", "uv_idx", "face_to_valid_tet", "valid_vert_idx"], out):
+        assert tuple(a.shape) == tuple(gold[f"sphere_{n}_shape"]), n
+        if a.dtype.kind in "iu":
+            digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype="<i8").tobytes()).digest(), dtype=np.uint8)
+            assert np.array_equal(digest, gold[f"sphere_{n}_sha256"]), n
+        else:
+            assert np.allclose(a[gold[f"sphere_{n}_rows"]], gold[f"sphere_{n}_sample"], rtol=1e-6, atol=1e-7), n
+
+
 def test_grid_mask_from_tets_has_reference_population():
     from meshdiffusion_b200.geometry import dmtet
     m = dmtet.grid_mask_from_tets(64)
