@@ -62,7 +62,6 @@ def build_state(config, rank=0, world=1):
     generator is seeded with config.seed before the model is created and re-seeded with seed + rank afterwards, so labels,
     noise and dropout differ per rank), and rank 0's parameters, buffers and EMA are broadcast on top, so replicas that only
     exchange gradients stay identical."""
-    import torch.distributed as dist
     seed = int(config.get("seed", 42))
     torch.manual_seed(seed)
     score_model = mutils.create_model(config)

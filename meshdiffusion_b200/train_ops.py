@@ -6,8 +6,6 @@ of the reference), global-norm clipping + Adam (losses.py:26-52) and the EMA upd
 native multi-tensor pass applies the clip coefficient, the Adam update and, when an EMA is handed in, its update too
 (the reference makes ~6 passes over the 364 M parameters). There is no CPU path: stepping CPU parameters raises.
 """
-import ctypes
-
 import numpy as np
 import torch
 
