@@ -255,7 +255,7 @@ def sampler_leg(ctx, precision, B, R, K, W, dump_profile=None, full_run=False):
 def ncu_traffic(precision):
     """dram read+write bytes per launch of the dominant launch type (128->128 conv @64^3) from the committed `ncu --set full`
     capture of this mode (taken at batch 8; reported as captured, with its batch and source file), or null."""
-    name = {"bf16": "r02_ncu_conv_bf16.txt", "bf16x3": "r02_ncu_conv_x3.txt", "tf32": "r02_ncu_conv_tf32.txt"}[precision]
+    name = {"bf16": "r02_ncu_conv_final_bf16.txt", "bf16x3": "r02_ncu_conv_final_bf16x3.txt", "tf32": "r02_ncu_conv_final_tf32.txt"}[precision]
     path = os.path.join(ROOT, "profiles", name)
     try:
         rd = wr = None
