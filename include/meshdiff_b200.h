@@ -221,6 +221,16 @@ int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batc
                               float* verts, long long* faces, long long* uv_idx, long long* face_to_tet,
                               long long* valid_vert_idx, const long long* vert_off, const long long* face_off,
                               const long long* vv_off, void* stream);
+/* Backward of the vertex interpolation: what torch autograd computes for DMTet.__call__'s `verts` with respect to `pos_nx3`
+ * and `sdf_n` (nvdiffrec/lib/geometry/dmtet.py:125-132 under loss.backward(); every other output is an integer tensor).
+ * grad_verts fp32 packed like `verts`; vert_off device int64 [B] (NULL = the offsets of the last phase 1); vertex_ids device
+ * uint32 [B][n_edges] = crossing edge -> output row, as copied by mdb_marching_tets_vertex_ids after the forward extract
+ * (NULL = the last extract's, still held by the handle). grad_pos fp32 [B][n_verts][3] and grad_sdf fp32 [B][n_verts] are
+ * overwritten (either may be NULL). A gather per grid vertex over its incident edges: no atomics, bitwise reproducible. */
+int mdb_marching_tets_vertex_ids(void* handle, int batch, unsigned* out, void* stream);
+int mdb_marching_tets_backward(void* handle, const float* pos, long long pos_batch_stride, const float* sdf, int batch,
+                               const unsigned* vertex_ids, const float* grad_verts, const long long* vert_off,
+                               float* grad_pos, float* grad_sdf, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mesh post-ops after marching tets. Scatter-adds run as 2^-40 fixed-point integer atomics: results are

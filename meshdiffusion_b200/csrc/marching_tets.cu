@@ -44,6 +44,8 @@ struct Handle {
   int* d_tets = nullptr;      // [F][4]
   int2* d_edges = nullptr;    // [E] sorted (a<b), lexicographic
   int* d_tet_edges = nullptr; // [F][6] edge ids in base_tet_edges order
+  int* d_vadj_off = nullptr;  // [Nv + 1] CSR of the edges incident to every grid vertex (backward pass)
+  int* d_vadj = nullptr;      // [2 E]   2 * edge id + (0: the vertex is the edge's first endpoint, 1: its second)
   // per-call workspace (sized for max_batch)
   uint8_t* d_eflag = nullptr;    // [B][E]  edge crosses the surface
   uint32_t* d_escan = nullptr;   // [B][E]  vertex id of a crossing edge (exclusive prefix sum of eflag)
@@ -292,6 +294,55 @@ __global__ void __launch_bounds__(256) mt_emit_valid_verts_kernel(const uint8_t*
   for (int i = 0; i < 8; ++i) if (f[i]) o[run++] = base + i;
 }
 
+// ---------------------------------------------------------------- backward of the vertex interpolation
+// What torch autograd computes for dmtet.py:125-132: with s_a = sdf[a], t = -sdf[b], den = s_a + t, the surface vertex of a
+// crossing edge (a, b) is v = p_a * (t / den) + p_b * (s_a / den). For g = dL/dv:
+//     dL/dp_a = g * t / den          dL/dp_b = g * s_a / den
+//     dL/dsdf[a] = g.(p_b - p_a) * t / den^2       dL/dsdf[b] = g.(p_b - p_a) * s_a / den^2   (= own weight / den)
+// One thread per grid vertex GATHERS over its incident edges (static CSR), in table order: no atomics, the sums are
+// bitwise reproducible. vid = the crossing edge's output row (the exclusive scan the forward pass left / the caller kept).
+__global__ void __launch_bounds__(256) mt_grad_kernel(const int2* __restrict__ edges, const int* __restrict__ vadj_off,
+                                                     const int* __restrict__ vadj, const uint32_t* __restrict__ vid,
+                                                     const float* __restrict__ pos, long long pos_bstride,
+                                                     const float* __restrict__ sdf, const float* __restrict__ gverts,
+                                                     const long long* __restrict__ vert_off, float* __restrict__ gpos,
+                                                     float* __restrict__ gsdf, int E, int Nv) {
+  const int b = blockIdx.y;
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= Nv) return;
+  const float* s = sdf + (size_t)b * Nv;
+  const float* p = pos + (size_t)b * pos_bstride;
+  const float* g = gverts + vert_off[b] * 3;
+  const uint32_t* id = vid + (size_t)b * E;
+  const float sv = s[v];
+  const bool occ = sv > 0.f;
+  float gx = 0.f, gy = 0.f, gz = 0.f, gs = 0.f;
+  const int k1 = __ldg(vadj_off + v + 1);
+  for (int k = __ldg(vadj_off + v); k < k1; ++k) {
+    const int code = __ldg(vadj + k);
+    const int e = code >> 1;
+    const int2 ab = __ldg(edges + e);
+    const int other = (code & 1) ? ab.x : ab.y;
+    const float so = s[other];
+    if ((so > 0.f) == occ) continue;  // not a crossing edge
+    const float sa = (code & 1) ? so : sv, t = (code & 1) ? -sv : -so;
+    const float den = sa + t;
+    const float w = ((code & 1) ? sa : t) / den;  // interpolation weight of THIS endpoint; d v / d sdf[this] = (p_b - p_a) * w / den
+    const float* gr = g + (size_t)id[e] * 3;
+    const float g0 = gr[0], g1 = gr[1], g2 = gr[2];
+    gx = fmaf(g0, w, gx); gy = fmaf(g1, w, gy); gz = fmaf(g2, w, gz);
+    const float* pa = p + (size_t)ab.x * 3;
+    const float* pb = p + (size_t)ab.y * 3;
+    const float dot = g0 * (pb[0] - pa[0]) + g1 * (pb[1] - pa[1]) + g2 * (pb[2] - pa[2]);
+    gs = fmaf(dot, w / den, gs);
+  }
+  if (gpos) {
+    float* o = gpos + ((size_t)b * Nv + v) * 3;
+    o[0] = gx; o[1] = gy; o[2] = gz;
+  }
+  if (gsdf) gsdf[(size_t)b * Nv + v] = gs;
+}
+
 static int grid1d(int n) { int g = (n + 255) / 256; return g > 148 * 4 ? 148 * 4 : (g < 1 ? 1 : g); }
 
 }  // namespace mdbmt
@@ -349,7 +400,19 @@ int mdb_marching_tets_prepare(const int* tets_host, int F, int Nv, int max_batch
   std::vector<int> te((size_t)F * 6);
   for (size_t i = 0; i < keys.size(); ++i)
     te[i] = (int)(std::lower_bound(uniq.begin(), uniq.end(), keys[i]) - uniq.begin());
+  // vertex -> incident edges (CSR, edges in table order): the gather form of the backward pass
+  std::vector<int> adj_off((size_t)Nv + 1, 0), adj((size_t)2 * h->E);
+  for (int e = 0; e < h->E; ++e) { adj_off[edges[e].x + 1]++; adj_off[edges[e].y + 1]++; }
+  for (int v = 0; v < Nv; ++v) adj_off[v + 1] += adj_off[v];
+  {
+    std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
+    for (int e = 0; e < h->E; ++e) { adj[fill[edges[e].x]++] = 2 * e; adj[fill[edges[e].y]++] = 2 * e + 1; }
+  }
   const size_t B = max_batch;
+  MT_CHECK(cudaMalloc(&h->d_vadj_off, ((size_t)Nv + 1) * 4));
+  MT_CHECK(cudaMalloc(&h->d_vadj, (size_t)2 * h->E * 4 + 4));
+  MT_CHECK(cudaMemcpy(h->d_vadj_off, adj_off.data(), ((size_t)Nv + 1) * 4, cudaMemcpyHostToDevice));
+  MT_CHECK(cudaMemcpy(h->d_vadj, adj.data(), (size_t)2 * h->E * 4, cudaMemcpyHostToDevice));
   MT_CHECK(cudaMalloc(&h->d_tets, (size_t)F * 16));
   MT_CHECK(cudaMalloc(&h->d_edges, (size_t)h->E * 8));
   MT_CHECK(cudaMalloc(&h->d_tet_edges, (size_t)F * 24));
@@ -371,7 +434,7 @@ int mdb_marching_tets_prepare(const int* tets_host, int F, int Nv, int max_batch
 void mdb_marching_tets_destroy(void* handle) {
   auto* h = static_cast<Handle*>(handle);
   if (!h) return;
-  cudaFree(h->d_tets); cudaFree(h->d_edges); cudaFree(h->d_tet_edges);
+  cudaFree(h->d_tets); cudaFree(h->d_edges); cudaFree(h->d_tet_edges); cudaFree(h->d_vadj_off); cudaFree(h->d_vadj);
   cudaFree(h->d_eflag); cudaFree(h->d_escan); cudaFree(h->d_vflag);
   cudaFree(h->d_tetidx); cudaFree(h->d_partials); cudaFree(h->d_counts); cudaFree(h->d_offs); cudaFreeHost(h->h_counts);
   delete h;
@@ -446,6 +509,35 @@ int mdb_marching_tets_extract(void* handle, const float* pos, long long pos_batc
   mt_emit_faces_kernel<<<dim3(h->tF, batch), 256, 0, s>>>(h->d_tet_edges, h->d_tetidx, h->d_partials, h->d_escan, h->d_counts, faces,
                                                           uv_idx, face_to_tet, face_off, F, E, h->tE, h->tF, pt);
   mt_emit_valid_verts_kernel<<<dim3(h->tV, batch), 256, 0, s>>>(h->d_vflag, h->d_partials, valid_vert_idx, vv_off, Nv, h->tE, h->tF, pt);
+  MT_CHECK(cudaGetLastError());
+  MT_API_END
+}
+
+/* Copies the crossing-edge -> output-row map of the last mdb_marching_tets_extract ([batch][n_edges] uint32) so that a
+ * backward pass can run after the handle has been used for another batch. */
+int mdb_marching_tets_vertex_ids(void* handle, int batch, unsigned* out, void* stream) {
+  MT_API_BEGIN
+  auto* h = static_cast<Handle*>(handle);
+  if (batch != h->last_batch) throw std::runtime_error("mdb MT: vertex ids are those of the last extract; batch differs");
+  MT_CHECK(cudaMemcpyAsync(out, h->d_escan, (size_t)batch * h->E * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  MT_API_END
+}
+
+/* Backward of the vertex interpolation (what autograd does for dmtet.py:125-132). */
+int mdb_marching_tets_backward(void* handle, const float* pos, long long pos_batch_stride, const float* sdf, int batch,
+                               const unsigned* vertex_ids, const float* grad_verts, const long long* vert_off,
+                               float* grad_pos, float* grad_sdf, void* stream) {
+  MT_API_BEGIN
+  auto* h = static_cast<Handle*>(handle);
+  if (batch < 1 || batch > h->max_batch) throw std::runtime_error("mdb MT: batch out of range");
+  if (!vertex_ids || !vert_off) {
+    if (batch != h->last_batch) throw std::runtime_error("mdb MT: backward without saved vertex ids needs the batch of the last extract");
+    if (!vertex_ids) vertex_ids = h->d_escan;
+    if (!vert_off) vert_off = h->d_offs;
+  }
+  mt_grad_kernel<<<dim3((h->Nv + 255) / 256, batch), 256, 0, (cudaStream_t)stream>>>(
+      h->d_edges, h->d_vadj_off, h->d_vadj, vertex_ids, pos, pos_batch_stride, sdf, grad_verts, vert_off, grad_pos, grad_sdf,
+      h->E, h->Nv);
   MT_CHECK(cudaGetLastError());
   MT_API_END
 }

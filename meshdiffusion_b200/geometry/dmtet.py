@@ -58,6 +58,7 @@ class MarchingTets:
         L.mdb_marching_tets_info(self._h, ctypes.byref(e), ctypes.byref(n))
         self.n_edges, self.uv_n = e.value, n.value
         self._uvs = None
+        self._last_off = None
 
     def __del__(self):
         try:
@@ -74,13 +75,10 @@ class MarchingTets:
             self._uvs = u
         return self._uvs
 
-    def extract(self, pos, sdf):
-        """pos [B,Nv,3] or [Nv,3] (shared), sdf [B,Nv] fp32 cuda -> list of per-sample
-        (verts, faces, uvs, uv_idx, face_to_valid_tet, valid_vert_idx)."""
+    def _extract_raw(self, pos, sdf):
+        """Packed outputs of the batch + the [B+1, 3] host table of (verts, faces, valid verts) offsets."""
         L = _native.lib()
-        sdf = sdf.float().contiguous()
         B = sdf.shape[0]
-        pos = pos.float().contiguous()
         stride = 0 if pos.dim() == 2 else self.Nv * 3
         counts = (ctypes.c_int * (3 * B))()
         stream = _native.current_stream()
@@ -97,7 +95,21 @@ class MarchingTets:
         _native.check(L.mdb_marching_tets_extract(self._h, _native.ptr(pos), stride, _native.ptr(sdf), B, _native.ptr(verts),
                                                   _native.ptr(faces), _native.ptr(uv_idx), _native.ptr(f2t), _native.ptr(vvi),
                                                   None, None, None, stream))
-        uvs = self.uvs(dev)
+        return verts, faces, uv_idx, f2t, vvi, off
+
+    def extract(self, pos, sdf):
+        """pos [B,Nv,3] or [Nv,3] (shared), sdf [B,Nv] fp32 cuda -> list of per-sample
+        (verts, faces, uvs, uv_idx, face_to_valid_tet, valid_vert_idx). `verts` is differentiable with respect to `pos`
+        and `sdf` like the reference's (autograd through dmtet.py:125-132); the other outputs are integer tensors."""
+        sdf = sdf.float().contiguous()
+        pos = pos.float().contiguous()
+        B = sdf.shape[0]
+        if torch.is_grad_enabled() and (pos.requires_grad or sdf.requires_grad):
+            verts, faces, uv_idx, f2t, vvi = _ExtractFn.apply(self, pos, sdf)
+            off = self._last_off
+        else:
+            verts, faces, uv_idx, f2t, vvi, off = self._extract_raw(pos.detach(), sdf.detach())
+        uvs = self.uvs(sdf.device)
         out = []
         for b in range(B):
             v0, v1 = off[b, 0], off[b + 1, 0]
@@ -105,6 +117,41 @@ class MarchingTets:
             w0, w1 = off[b, 2], off[b + 1, 2]
             out.append((verts[v0:v1], faces[f0:f1], uvs, uv_idx[f0:f1], f2t[f0:f1], vvi[w0:w1]))
         return out
+
+
+class _ExtractFn(torch.autograd.Function):
+    """Marching tets as one autograd node: the backward pass is `mdb_marching_tets_backward` (a gather per grid vertex over
+    its incident crossing edges), fed by the crossing-edge -> output-row map saved from the forward pass."""
+
+    @staticmethod
+    def forward(ctx, mt, pos, sdf):
+        verts, faces, uv_idx, f2t, vvi, off = mt._extract_raw(pos, sdf)
+        B = sdf.shape[0]
+        vid = torch.empty(B, mt.n_edges, device=sdf.device, dtype=torch.int32)
+        _native.check(_native.lib().mdb_marching_tets_vertex_ids(mt._h, B, _native.ptr(vid), _native.current_stream()))
+        voff = torch.from_numpy(np.ascontiguousarray(off[:-1, 0])).to(sdf.device)
+        ctx.mt = mt
+        ctx.save_for_backward(pos, sdf, vid, voff)
+        ctx.mark_non_differentiable(faces, uv_idx, f2t, vvi)
+        mt._last_off = off
+        return verts, faces, uv_idx, f2t, vvi
+
+    @staticmethod
+    def backward(ctx, gverts, *_unused):
+        pos, sdf, vid, voff = ctx.saved_tensors
+        mt = ctx.mt
+        B = sdf.shape[0]
+        need_pos, need_sdf = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gpos = torch.empty(B, mt.Nv, 3, device=sdf.device, dtype=torch.float32) if need_pos else None
+        gsdf = torch.empty(B, mt.Nv, device=sdf.device, dtype=torch.float32) if need_sdf else None
+        stride = 0 if pos.dim() == 2 else mt.Nv * 3
+        gverts = gverts.float().contiguous()
+        _native.check(_native.lib().mdb_marching_tets_backward(mt._h, _native.ptr(pos), stride, _native.ptr(sdf), B, _native.ptr(vid),
+                                                               _native.ptr(gverts), _native.ptr(voff), _native.ptr(gpos),
+                                                               _native.ptr(gsdf), _native.current_stream()))
+        if need_pos and pos.dim() == 2:
+            gpos = gpos.sum(0)  # one vertex array shared by the batch
+        return None, gpos, gsdf
 
 
 class DMTet:

@@ -341,6 +341,7 @@ def golden_marching_tets():
         cases[case + "_uvs_tail"] = r[2][-64:]
         cases[case + "_uvs_sum"] = np.array([r[2].astype(np.float64).sum()])
     np.savez_compressed(os.path.join(GOLD, "marching_tets_64.npz"), **cases)
+    golden_marching_tets_grad(mt, verts, idx)
     golden_marching_tets_128(mt)
     # grid mask derivable from the tet grid (data/get_tet_mask.py): check against the shipped mask
     coords = mt_oracle.grid_coords_of_tet_vertices(verts)
@@ -349,6 +350,32 @@ def golden_marching_tets():
     ref_mask = torch.load(os.path.join(REF, "data/grid_mask_64.pt"), map_location="cpu").numpy()
     assert np.array_equal(mask, ref_mask), "grid mask derived from the tet grid differs from data/grid_mask_64.pt"
     print("grid_mask_64 == scatter of tet vertices:", int(mask.sum()), "voxels")
+
+
+def golden_marching_tets_grad(mt, verts, idx):
+    """tests/golden/marching_tets_64_grad.npz: gradients of the REFERENCE DMTet's `verts` with respect to pos_nx3 and sdf_n
+    (torch autograd through dmtet.py:125-132, L = sum(verts * W)); the numpy restatement must agree. The sdf of both cases is
+    continuous here (the sign() of the sampling path has no gradient): sphere, and sphere + noise with deformed vertices."""
+    cases = {}
+    for case, seed in (("sphere", 0), ("noisy", 1)):
+        sdf, pos = synth.synthetic_dmtet_grad_case(verts, seed=seed, noisy=(case == "noisy"))
+        p = torch.tensor(pos, requires_grad=True)
+        s = torch.tensor(sdf, requires_grad=True)
+        v = mt(p, s, torch.tensor(idx).long())[0]
+        W = synth.mt_grad_weights(v.shape[0], seed)
+        (v * torch.tensor(W)).sum().backward()
+        gp, gs = p.grad.numpy(), s.grad.numpy()
+        op, os_ = mt_oracle.marching_tets_vertex_grad(pos, sdf, idx, W)
+        sp, ss = np.abs(gp).max(), np.abs(gs).max()
+        assert np.abs(gp - op).max() <= 1e-5 * sp and np.abs(gs - os_).max() <= 1e-5 * ss, (case, np.abs(gp - op).max() / sp, np.abs(gs - os_).max() / ss)
+        print(f"marching tets grad {case}: {v.shape[0]} verts, |dpos| max {sp:.3g}, |dsdf| max {ss:.3g} -- oracle == reference autograd")
+        nzp, nzs = np.flatnonzero(np.abs(gp).sum(1)), np.flatnonzero(gs)
+        cases[case + "_n_verts"] = np.array([v.shape[0]])
+        cases[case + "_pos_rows"] = nzp.astype(np.int32)
+        cases[case + "_grad_pos"] = gp[nzp]
+        cases[case + "_sdf_rows"] = nzs.astype(np.int32)
+        cases[case + "_grad_sdf"] = gs[nzs]
+    np.savez_compressed(os.path.join(GOLD, "marching_tets_64_grad.npz"), **cases)
 
 
 def golden_dataset_items():

@@ -59,6 +59,35 @@ def marching_tets(pos, sdf, tets):
     return verts, faces, uvs, uv_idx, face_to_valid_tet, valid_vert_idx
 
 
+def marching_tets_vertex_grad(pos, sdf, tets, grad_verts):
+    """What torch autograd returns for d(sum(verts * grad_verts)) / d(pos, sdf) through dmtet.py:125-132 (float64 inside):
+    v = (p_a * (-s_b) + p_b * s_a) / (s_a - s_b) on every crossing edge (a < b) of the sorted unique edge list."""
+    pos = np.asarray(pos, np.float64)
+    sdf = np.asarray(sdf, np.float64)
+    tets = np.asarray(tets, np.int64)
+    g = np.asarray(grad_verts, np.float64)
+    occ = np.asarray(sdf, np.float32) > 0
+    occ4 = occ[tets.reshape(-1)].reshape(-1, 4)
+    occ_sum = occ4.sum(-1)
+    valid = (occ_sum > 0) & (occ_sum < 4)
+    edges = tets[valid][:, BASE_TET_EDGES].reshape(-1, 2)
+    edges = np.stack([edges.min(1), edges.max(1)], -1)
+    uniq = np.unique(edges, axis=0)
+    ev = uniq[occ[uniq.reshape(-1)].reshape(-1, 2).sum(-1) == 1]
+    a, b = ev[:, 0], ev[:, 1]
+    sa, t = sdf[a], -sdf[b]
+    den = sa + t
+    wa, wb = t / den, sa / den
+    gpos = np.zeros_like(pos)
+    np.add.at(gpos, a, g * wa[:, None])
+    np.add.at(gpos, b, g * wb[:, None])
+    dot = (g * (pos[b] - pos[a])).sum(-1)
+    gsdf = np.zeros_like(sdf)
+    np.add.at(gsdf, a, dot * t / den ** 2)
+    np.add.at(gsdf, b, dot * sa / den ** 2)
+    return gpos.astype(np.float32), gsdf.astype(np.float32)
+
+
 def uv_grid_n(max_idx):
     return int(np.ceil(np.sqrt((max_idx + 1) // 2)))
 

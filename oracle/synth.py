@@ -75,3 +75,17 @@ def synthetic_dmtet(vertices, seed, noisy, res=64):
     sdf = np.sign(sdf).astype(np.float32) if noisy else sdf
     pos = (v * np.float32(1.1) + np.float32(2 / (res * 2)) * deform * np.float32(3.0)).astype(np.float32)
     return sdf, pos
+
+
+def synthetic_dmtet_grad_case(vertices, seed, noisy):
+    """Inputs of the marching-tet GRADIENT goldens: as synthetic_dmtet, but the noisy case keeps a continuous sdf (its signs
+    with varying magnitudes; zeros stay zero) -- the sign() field of the sampling path has no gradient to check."""
+    sdf, pos = synthetic_dmtet(vertices, seed=seed, noisy=noisy)
+    if noisy:
+        sdf = (sdf * (0.05 + np.random.RandomState(7).rand(sdf.shape[0]))).astype(np.float32)
+    return sdf, pos
+
+
+def mt_grad_weights(n_verts, seed):
+    """dL/dverts of the marching-tet gradient goldens: L = sum(verts * W)."""
+    return np.random.RandomState(100 + seed).randn(n_verts, 3).astype(np.float32)

@@ -62,6 +62,29 @@ def test_marching_tets_oracle_matches_reference_golden():
         assert tuple(uvs.shape) == tuple(gold[case + "_uvs_shape"])
 
 
+def _dense_grad(gold, case, n_verts):
+    gp = np.zeros((n_verts, 3), np.float32)
+    gs = np.zeros(n_verts, np.float32)
+    gp[gold[case + "_pos_rows"]] = gold[case + "_grad_pos"]
+    gs[gold[case + "_sdf_rows"]] = gold[case + "_grad_sdf"]
+    return gp, gs
+
+
+def test_marching_tets_gradient_oracle_matches_reference_autograd():
+    """d(sum(verts * W)) / d(pos, sdf) of the numpy restatement vs torch autograd through the REFERENCE DMTet
+    (oracle/make_golden.py::golden_marching_tets_grad)."""
+    from meshdiffusion_b200.geometry import dmtet
+    gold = load_golden("marching_tets_64_grad.npz")
+    verts, idx = dmtet.load_tet_grid(64)
+    for case, seed in (("sphere", 0), ("noisy", 1)):
+        sdf, pos = synth.synthetic_dmtet_grad_case(verts, seed=seed, noisy=(case == "noisy"))
+        W = synth.mt_grad_weights(int(gold[case + "_n_verts"][0]), seed)
+        gp, gs = mt_oracle.marching_tets_vertex_grad(pos, sdf, idx, W)
+        rp, rs = _dense_grad(gold, case, verts.shape[0])
+        assert np.abs(gp - rp).max() <= 1e-5 * np.abs(rp).max()
+        assert np.abs(gs - rs).max() <= 1e-5 * np.abs(rs).max()
+
+
 def test_marching_tets_oracle_matches_reference_golden_128():
     """The R=128 grid (1.39 M tets): the oracle's integer outputs hash to the digests the REFERENCE DMTet class produced."""
     import hashlib
