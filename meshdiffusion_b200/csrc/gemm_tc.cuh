@@ -321,6 +321,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     x0 = xt * p.bx; y0 = yt * p.by; z0 = zt * p.bz; b0 = bt * p.bb;
   };
 
+  // Warpgroup 0 = warps 0-3 (TMA producer, MMA issuer, TMEM allocator, one idle warp); warpgroups 1-2 = the epilogue.
+  // GNB only: the GroupNorm-backward epilogue is the long pole of that instantiation and it is latency-bound at 168 registers
+  // (ncu source page, profiles/r02_ncu_gnb_before.txt: local-memory reloads, re-materialised S2R / LDCU, exposed constant
+  // loads), so warpgroup 0 hands registers to the epilogue warpgroups: 128 x kRegsLo + 256 x kRegsHi <= 65 536. Each
+  // setmaxnreg is the first instruction of its warpgroup's branch, so ptxas allocates every role with its own limit.
+  constexpr int kRegsLo = 72, kRegsHi = 216;
+  if (warp < 4) {
+  if constexpr (GNB) setmaxnreg_dec<kRegsLo>();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t st = 0, ph = 0;
@@ -496,7 +504,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
       if (elect_one()) { if constexpr (CG2) umma_commit_pair(t_full + 8 * acc); else umma_commit(t_full + 8 * acc); }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if constexpr (GNB) setmaxnreg_inc<kRegsHi>();
     // ------------------------------------------------------------------ epilogue
     // 8 epilogue warps: warp w reads TMEM lanes 32*(w%4).. (hardware rule) and owns the column chunks
     // {half, half+2, ...}; two warps per lane quarter double the latency hiding of the drain.
