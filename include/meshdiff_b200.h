@@ -54,6 +54,10 @@ int mdb_unet_param_info(mdb_unet* net, int idx, const char** name, long long* nu
 /* load_state_dict: copy one tensor in (src on host if src_is_device == 0). */
 int mdb_unet_set_param(mdb_unet* net, const char* name, const float* src, long long numel, int src_is_device,
                        void* stream);
+/* The same for `count` DEVICE tensors in one call (the training step re-uploads all ~500 master parameters after every
+ * optimiser step, losses.py:26-52: one host call instead of 500). */
+int mdb_unet_set_params(mdb_unet* net, int count, const char* const* names, const float* const* srcs, const long long* numels,
+                        void* stream);
 /* state_dict: copy one tensor out; synchronises the stream. */
 int mdb_unet_get_param(mdb_unet* net, const char* name, float* dst, long long numel, int dst_is_device, void* stream);
 /* Re-derive packed weights / constant stem field after parameters changed; synchronises the stream. */

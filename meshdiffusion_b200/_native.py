@@ -57,6 +57,7 @@ SIGNATURES = {
     "mdb_unet_set_param": (_i, [_vp, ctypes.c_char_p, _vp, _ll, _i, _vp]),
     "mdb_unet_get_param": (_i, [_vp, ctypes.c_char_p, _vp, _ll, _i, _vp]),
     "mdb_unet_commit": (_i, [_vp, _vp]),
+    "mdb_unet_set_params": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "mdb_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "mdb_unet_info": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(_ll), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "mdb_unet_profile": (_i, [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_char_p, _i, ctypes.POINTER(_f), _i, ctypes.POINTER(_i)]),

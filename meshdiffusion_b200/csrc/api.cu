@@ -75,6 +75,13 @@ int mdb_unet_set_param(mdb_unet* n, const char* name, const float* src, long lon
   MDB_API_END
 }
 
+int mdb_unet_set_params(mdb_unet* n, int count, const char* const* names, const float* const* srcs, const long long* numels,
+                        void* stream) {
+  MDB_API_BEGIN
+  for (int i = 0; i < count; ++i) n->net->set_param(names[i], srcs[i], numels[i], true, (cudaStream_t)stream);
+  MDB_API_END
+}
+
 int mdb_unet_get_param(mdb_unet* n, const char* name, float* dst, long long numel, int dev, void* stream) {
   MDB_API_BEGIN
   n->net->get_param(name, dst, numel, dev != 0, (cudaStream_t)stream);

@@ -288,14 +288,39 @@ class ScoreNet(nn.Module):
         if changed is not None and not changed:
             return fp
         stream = _native.current_stream()
-        for i, n in enumerate(self._names):
-            if changed is not None and i not in changed:
-                continue
-            src = self._param(n).detach().float().contiguous()
-            _native.check(L.mdb_unet_set_param(handle, n.encode(), _native.ptr(src), src.numel(), 1 if src.is_cuda else 0, stream))
+        self._upload(handle, range(len(self._names)) if changed is None else changed, stream)
         torch.cuda.current_stream().synchronize()
         _native.check(L.mdb_unet_commit(handle, stream))
         return fp
+
+    def _upload(self, handle, indices, stream):
+        """Copies the given master parameters into the engine: fp32 contiguous CUDA tensors go through ONE
+        mdb_unet_set_params call (argument arrays cached per (index set, storage addresses): the training step re-uploads
+        every parameter after every optimiser step); anything else (host tensors, other dtypes) one by one."""
+        import ctypes
+        L = _native.lib()
+        indices = tuple(indices)
+        params = [self._param(self._names[i]) for i in indices]
+        bulk = [k for k, p in enumerate(params) if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()]
+        if bulk:
+            key = (tuple(indices[k] for k in bulk), tuple(params[k].data_ptr() for k in bulk))
+            cache = getattr(self, "_upload_cache", None)
+            if cache is None or cache[0] != key:
+                m = len(bulk)
+                names = (ctypes.c_char_p * m)(*[self._names[indices[k]].encode() for k in bulk])
+                srcs = (ctypes.c_void_p * m)(*key[1])
+                numels = (ctypes.c_longlong * m)(*[params[k].numel() for k in bulk])
+                cache = self._upload_cache = (key, m, names, srcs, numels)
+            _native.check(L.mdb_unet_set_params(handle, cache[1], cache[2], cache[3], cache[4], stream))
+        done = set(bulk)
+        for k, p in enumerate(params):
+            if k in done:
+                continue
+            src = p.detach().float().contiguous()
+            _native.check(L.mdb_unet_set_param(handle, self._names[indices[k]].encode(), _native.ptr(src), src.numel(),
+                                               1 if src.is_cuda else 0, stream))
+            if src.is_cuda:
+                src.record_stream(torch.cuda.current_stream())
 
     def _train_forward(self, x, labels):
         L = _native.lib()
@@ -412,12 +437,7 @@ class ScoreNet(nn.Module):
         if changed is not None and not changed:
             return
         stream = _native.current_stream()
-        for i, n in enumerate(self._names):
-            if changed is not None and i not in changed:
-                continue
-            src = self._param(n).detach().float().contiguous()
-            _native.check(L.mdb_unet_set_param(self._handle, n.encode(), _native.ptr(src), src.numel(),
-                                               1 if src.is_cuda else 0, stream))
+        self._upload(self._handle, range(len(self._names)) if changed is None else changed, stream)
         torch.cuda.current_stream().synchronize()
         _native.check(L.mdb_unet_commit(self._handle, stream))
         self._synced = fp
