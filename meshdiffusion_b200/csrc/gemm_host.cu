@@ -398,18 +398,20 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const LoadEntry* __re
     const PackWSrc& w = args.w[e.wsrc];
     const long long noff = w.ndiv ? (long long)(n % w.ndiv) * w.sn + (long long)(n / w.ndiv) * w.sn_hi : (long long)n * w.sn;
     const int c0 = e.wc0 + v8 * 8;
-    long long coff[8];
+    long long coff[8];  // (may be negative: mirrored sources point at their last tap and walk backwards)
+    unsigned valid = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = c0 + i;
-      coff[i] = c >= w.cvalid ? -1 : noff + (w.cdiv ? (long long)(c % w.cdiv) * w.sc + (long long)(c / w.cdiv) * w.sc_hi : (long long)c * w.sc);
+      if (c < w.cvalid) valid |= 1u << i;
+      coff[i] = noff + (w.cdiv ? (long long)(c % w.cdiv) * w.sc + (long long)(c / w.cdiv) * w.sc_hi : (long long)c * w.sc);
     }
     const long long obase = ((long long)n * ksteps + load_ks0[l]) * KB + v8 * 8;
     for (int j = 0; j < e.nk; ++j) {
       const long long toff = (long long)(e.tap0 + j * e.tapj) * w.st;
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = coff[i] < 0 ? 0.f : __ldg(w.ptr + coff[i] + toff);
+      for (int i = 0; i < 8; ++i) v[i] = (valid >> i) & 1u ? __ldg(w.ptr + coff[i] + toff) : 0.f;
       const long long o = obase + (long long)j * KB;
       if (MODE == 1) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
