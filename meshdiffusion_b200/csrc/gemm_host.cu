@@ -104,7 +104,6 @@ void GemmOp::enable_splits(int S, float* scratch) {
 
 GemmOp::~GemmOp() {
   if (d_loads) cudaFree(d_loads);
-  if (d_ks2load) cudaFree(d_ks2load);
   if (d_ks0) cudaFree(d_ks0);
   if (d_wpacked && owns_w) cudaFree(d_wpacked);
 }

@@ -72,8 +72,7 @@ class GemmOp {
   int ksteps = 0;
   // device-owned
   LoadEntry* d_loads = nullptr;
-  int* d_ks2load = nullptr;  // (weight packer) k-step -> load entry, first k-step of each entry
-  int* d_ks0 = nullptr;
+  int* d_ks0 = nullptr;      // (weight packer) first k-step of every load entry
   void* d_wpacked = nullptr;  // [N][ksteps*KB] in activation dtype
   bool owns_w = false;
   double flops = 0;  // algorithmic FLOPs of one launch (2*M*N*K over valid taps, counted densely)

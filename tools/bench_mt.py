@@ -55,6 +55,28 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         res[name] = {"ms_per_batch": ms, "samples_per_s": B / (ms * 1e-3), "tets_per_s": B * F / (ms * 1e-3)}
+    # differentiable path: extract with autograd + the backward gather kernel (d sum(verts) / d(pos, sdf))
+    sdf_c = (sdf * (0.05 + torch.rand(B, Nv, device=dev, generator=g))).requires_grad_(True)
+    pos_g = pos.clone().requires_grad_(True)
+
+    def step_grad():
+        ms_ = mt.extract(pos_g, sdf_c)
+        loss = sum(m[0].sum() for m in ms_)
+        pos_g.grad = sdf_c.grad = None
+        loss.backward()
+
+    for _ in range(3):
+        step_grad()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_grad()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    res["extract+backward"] = {"ms_per_batch": ms, "samples_per_s": B / (ms * 1e-3),
+                               "note": "autograd node + mdb_marching_tets_backward (incl. the per-sample torch sum/slice ops of this loss)"}
     faces = sum(m[1].shape[0] for m in meshes)
     alg_bytes = B * (F * 16 + mt.n_edges * 8 + Nv * 16)
     ms = res["extract"]["ms_per_batch"]
