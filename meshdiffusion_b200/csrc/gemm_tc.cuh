@@ -520,6 +520,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int seg = row / rows_per_b;  // which sample of the tile this row belongs to (warp-uniform by construction)
     int it = 0;
     int staged_n0 = -1, staged_b0 = -1, bias_buf = 0;
+    // GNB: whether column sums are wanted is decided ONCE and pinned in a register. Re-reading the two pointers from the
+    // 4 KB parameter block in front of every chunk's reduction cost a constant-cache miss each time (ncu source page,
+    // profiles/r02_ncu_gnb_after.txt: 14 % of the epilogue warps' samples sat on that LDCU).
+    int want_cols = 0;
+    if constexpr (GNB) {
+      want_cols = (p.stats != nullptr || p.gnb_part != nullptr) ? 1 : 0;
+      asm volatile("" : "+r"(want_cols));
+    }
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -750,7 +758,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
             }
           }
         }
-        if (p.stats || (GNB && p.gnb_part)) {  // (never reached in split-K mode)
+        if (GNB ? (want_cols != 0) : (p.stats != nullptr)) {  // (never reached in split-K mode)
           // Column sums over the warp's 32 rows: butterfly transpose-reduce (31 shuffles per quantity);
           // afterwards lane i holds the sum of column i.
           float s[32], ss[32];
