@@ -520,9 +520,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int seg = row / rows_per_b;  // which sample of the tile this row belongs to (warp-uniform by construction)
     int it = 0;
     int staged_n0 = -1, staged_b0 = -1, bias_buf = 0;
-    // GNB: whether column sums are wanted is decided ONCE and pinned in a register. Re-reading the two pointers from the
-    // 4 KB parameter block in front of every chunk's reduction cost a constant-cache miss each time (ncu source page,
-    // profiles/r02_ncu_gnb_after.txt: 14 % of the epilogue warps' samples sat on that LDCU).
+    // GNB: whether column sums are wanted is decided ONCE and pinned in a register instead of re-reading two pointers of the
+    // 4 KB parameter block in front of every chunk's reduction (ncu source page, profiles/r02_ncu_gnb_after.txt: 14 % of the
+    // epilogue warps' samples sat on that LDCU; by CUDA events the gain is small, 1-2 % of the GNB launches).
     int want_cols = 0;
     if constexpr (GNB) {
       want_cols = (p.stats != nullptr || p.gnb_part != nullptr) ? 1 : 0;
