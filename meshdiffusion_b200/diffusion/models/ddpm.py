@@ -297,7 +297,6 @@ class ScoreNet(nn.Module):
         """Copies the given master parameters into the engine: fp32 contiguous CUDA tensors go through ONE
         mdb_unet_set_params call (argument arrays cached per (index set, storage addresses): the training step re-uploads
         every parameter after every optimiser step); anything else (host tensors, other dtypes) one by one."""
-        import ctypes
         L = _native.lib()
         indices = tuple(indices)
         params = [self._param(self._names[i]) for i in indices]
