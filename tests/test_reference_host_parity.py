@@ -70,6 +70,15 @@ for step in (0, 10, 4999, 20000):
     steps.append({"lr": opt.param_groups[0]["lr"], "w0": w[0].detach().double().flatten().tolist(), "w1": w[1].detach().double().tolist()})
 res["optim"] = {"steps": steps, "defaults": {k: (list(v) if isinstance(v, tuple) else v) for k, v in opt.defaults.items()
                                               if k in ("lr", "betas", "eps", "weight_decay", "amsgrad")}}
+res["sigmas"] = [float(v) for v in ref["mutils"].get_sigmas(config)]
+# initial weights of a tiny network (the reference's own initialisers): per-tensor statistics
+config.data.image_size, config.model.nf, config.model.ch_mult = 16, 32, (1, 2)
+config.model.num_res_blocks, config.model.attn_resolutions = 1, (8,)
+torch.manual_seed(5)
+m = ref["mutils"].create_model(config)
+res["init"] = {k: {"std": float(v.double().std()) if v.numel() > 1 else 0.0, "absmax": float(v.abs().max()), "mean": float(v.double().mean()),
+                   "numel": v.numel(), "const": bool((v == v.flatten()[0]).all())}
+               for k, v in m.state_dict().items() if v.dtype.is_floating_point and k.split(".")[-1] not in ("sigmas", "mask", "coords")}
 json.dump(res, open(out, "w"))
 print("REF_DONE")
 '''
@@ -166,3 +175,40 @@ def test_optimizer_defaults_equal_the_reference(ref):
     for step, rec in zip((0, 10, 4999, 20000), ref["optim"]["steps"]):
         want = cfg.optim.lr * min(step / cfg.optim.warmup, 1.0) if cfg.optim.warmup > 0 else cfg.optim.lr
         assert abs(rec["lr"] - want) <= 1e-12 * max(abs(want), 1e-30), (step, rec["lr"], want)
+
+
+def test_sigmas_buffer_equals_the_reference(ref):
+    from configs import res64
+    from meshdiffusion_b200.diffusion.models import utils as mutils
+    ours = mutils.get_sigmas(res64.get_config())
+    assert np.array_equal(np.asarray(ours, dtype=np.float64), np.array(ref["sigmas"]))
+
+
+def test_initialisers_match_the_reference_layer_by_layer(ref):
+    """`create_model` draws every tensor from the distribution the reference's constructors use (default_init = variance
+    scaling, fan_avg, uniform -- layers.py:54-91; zero-scale Conv_1 / NIN_3 / head; nn.Linear / GroupNorm / bias defaults):
+    constant tensors are equal, random ones agree in spread and range (the RNG streams differ: the reference draws and then
+    overwrites torch's own Conv3d initialisation)."""
+    from helpers import tiny_config
+    from meshdiffusion_b200.diffusion.models import utils as mutils
+    cfg = tiny_config()
+    cfg.device = torch.device("cpu")
+    torch.manual_seed(5)
+    sd = mutils.create_model(cfg).state_dict()
+    theirs = ref["init"]
+    assert set(theirs) <= set(sd)
+    checked = 0
+    for k, r in theirs.items():
+        v = sd[k]
+        assert v.numel() == r["numel"], k
+        if r["const"]:
+            assert bool((v == v.flatten()[0]).all()) and abs(float(v.flatten()[0]) - r["mean"]) <= 1e-12, k
+            continue
+        n = r["numel"]
+        tol = max(0.03, 10.0 * (0.2 / n) ** 0.5)
+        std = float(v.double().std())
+        assert abs(std / r["std"] - 1.0) < tol, (k, std, r["std"])
+        if r["absmax"] > 1e-6:  # a uniform law: the sample maximum sits just under the bound in both
+            assert abs(float(v.abs().max()) / r["absmax"] - 1.0) < max(0.05, 20.0 / n), (k, float(v.abs().max()), r["absmax"])
+        checked += 1
+    assert checked > 30
