@@ -322,3 +322,45 @@ def test_statistics_record_round_trip():
     # sums of many records stay exact in integer arithmetic (what the kernels' atomics do)
     many = ops.stats_to_words(torch.full((1, 1, 2), 40000.123, dtype=torch.float64)).repeat(1, 1000, 1).sum(dim=1, keepdim=True)
     assert torch.allclose(ops.words_to_stats(many), torch.full((1, 1, 2), 40000.123 * 1000, dtype=torch.float64), rtol=1e-9)
+
+
+def test_trainer_loop_bounds_checkpoint_names_and_resume(tmp_path, monkeypatch):
+    """The host loop of `--mode=train` with a stubbed optimiser step (the real one needs the GPU): iterations
+    range(initial_step // iter_size, n_iters + 1), flags (clear_grad on the first, update_param on the last micro-batch),
+    `checkpoint_<step>.pth` every snapshot_freq AND at step == n_iters, the pre-emption file every
+    snapshot_freq_for_preemption, and auto-resume from it -- the reference's trainer.py:44-51,95-130."""
+    from meshdiffusion_b200.diffusion import trainer
+    cfg = tiny_config()
+    cfg.device = torch.device("cpu")
+    cfg.data.synthetic = True
+    cfg.training.train_dir = str(tmp_path / "run")
+    cfg.training.n_iters, cfg.training.iter_size, cfg.training.batch_size = 5, 2, 2
+    cfg.training.snapshot_freq, cfg.training.snapshot_freq_for_preemption, cfg.training.log_freq = 2, 3, 1
+    R = cfg.data.image_size
+    monkeypatch.setattr(trainer, "load_grid_mask", lambda r, dev: torch.ones(r, r, r))
+    monkeypatch.setattr(trainer, "synthetic_grids", lambda b, r, dev, gen=None: torch.zeros(b, 4, r, r, r))
+    calls = []
+
+    def fake_make_train_step(config, state, sde, mask):
+        def step_fn(state, batch, clear_grad=True, update_param=True):
+            assert tuple(batch.shape) == (2, 4, R, R, R)
+            calls.append((int(state["step"]), clear_grad, update_param))
+            state["step"] += 1  # losses.py:128 of the reference: the counter advances every micro-step
+            return {"loss": torch.tensor(1.0)}
+        return step_fn
+
+    monkeypatch.setattr(trainer, "make_train_step", fake_make_train_step)
+    trainer.train(cfg)
+    ck = os.path.join(cfg.training.train_dir, "checkpoints")
+    assert sorted(os.listdir(ck)) == ["checkpoint_2.pth", "checkpoint_4.pth", "checkpoint_5.pth"]
+    meta = os.path.join(cfg.training.train_dir, "checkpoints-meta", "checkpoint.pth")
+    assert os.path.exists(meta)
+    assert len(calls) == 6 * 2 and [c[1:] for c in calls[:2]] == [(True, False), (False, True)]
+    assert torch.load(os.path.join(ck, "checkpoint_5.pth"), weights_only=False)["step"] == 12
+    assert torch.load(meta, weights_only=False)["step"] == 8  # written after iteration 3 (4 iterations x 2 micro-steps)
+    # resume: the pre-emption file holds step 8 -> the loop restarts at iteration 8 // 2 = 4
+    calls.clear()
+    cfg.training.n_iters = 6
+    trainer.train(cfg)
+    assert [c[0] for c in calls] == [8, 9, 10, 11, 12, 13]
+    assert "checkpoint_6.pth" in os.listdir(ck)
