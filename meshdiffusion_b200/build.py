@@ -19,7 +19,19 @@ def _newest_mtime(paths):
 
 
 def build(force=False, verbose=False):
+    """Compiles the library unless it is newer than every source. Serialised by a file lock: under torchrun every rank may
+    find the library missing at the same moment; one compiles, the others wait and then see an up-to-date file."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "meshdiff_b200.h")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_mtime(deps):
